@@ -1,0 +1,193 @@
+/* libs2ag_b200.so -- C ABI of the B200-native Speech2AffectiveGestures GAN-step hot path.
+ *
+ * The reference (UttaranB127/speech2affective_gestures) has no FFI of its own: its boundary for
+ * this path is the Python module surface of net/multimodal_context_net_v2.py and
+ * processor_v2.py.  Each entry point below replaces the torch.nn operator
+ * call sites named in its comment (file:line are relative to the reference checkout); the
+ * Python mirror in speech2affective_gestures_b200/net/ binds them through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (fp32 unless stated otherwise);
+ *     workspaces are caller-provided, nothing is allocated, nothing synchronises the host;
+ *   - activations are CHANNELS-LAST: a Conv1d tensor the reference holds as [N, C, L] is
+ *     [N, L, C] here, a Conv2d tensor [N, C, T, V] is [N, T, V, C]; weights keep the
+ *     reference (PyTorch state_dict) layout unless stated;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 ok, <0 error (s2ag_last_error() has the text).  Never throws.
+ *   - "+=" in a comment: the kernel ACCUMULATES into that buffer (parameter gradients live in
+ *     one flat buffer per network that is zeroed once per optimiser step).
+ */
+#ifndef S2AG_H_
+#define S2AG_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int s2ag_version(void);
+const char* s2ag_last_error(void);
+/* 1 when the library was compiled from CUDA sources for sm_100a; the CPU logic-emulation build
+ * used by tests/emu reports 0 and is never loaded by the product path. */
+int s2ag_is_device_build(void);
+
+#define S2AG_ACT_NONE 0
+#define S2AG_ACT_RELU 1
+#define S2AG_ACT_LEAKY 2
+
+/* ---- nn.Linear (net/multimodal_context_net_v2.py:49,57,78,90,473-475,483-485,562-563) --------
+ * y[M,N] = act(x[M,K] @ w[N,K]^T + bias[N]); row strides ldx / ldy let x and y be column
+ * slices of wider buffers (the torch.cat at :526,:539 is never materialised). */
+int s2ag_linear_fwd(const float* x, long ldx, const float* w, const float* bias, float* y, long ldy,
+                    int M, int N, int K, int act, float slope, void* stream);
+/* dx[M,K] (+)= dy[M,N] @ w[N,K] */
+int s2ag_linear_bwd_data(const float* dy, long lddy, const float* w, float* dx, long lddx,
+                         int M, int N, int K, int accumulate, void* stream);
+/* dw[N,K] += dy^T x ; db[N] += colsum(dy) (db may be NULL) */
+int s2ag_linear_bwd_weight(const float* dy, long lddy, const float* x, long ldx, float* dw, float* db,
+                           int M, int N, int K, void* stream);
+/* dpre = dy * act'(y) evaluated from the activation OUTPUT y; [M,N] with row strides */
+int s2ag_act_bwd(const float* dy, long lddy, const float* y, long ldy, float* dpre, long ldd,
+                 int M, int N, int act, float slope, void* stream);
+/* y[M,H] = x[M, 0:H] + x[M, H:2H]  (sum of the bidirectional GRU halves, :542, :579) */
+int s2ag_add_halves(const float* x, float* y, int M, int H, void* stream);
+/* y = x * mask(seed)/(1-p) (nn.Dropout / nn.GRU inter-layer dropout); stateless counter RNG so
+ * the backward call regenerates the mask from the same seed. In-place allowed. */
+int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, void* stream);
+
+/* ---- nn.Conv1d / nn.Conv2d over channels-last activations -----------------------------------
+ * (WavEncoder :17-27, MFCCEncoder :39-45, AffEncoder :146-150, STGraphConv tgcn.py:64-68,
+ *  181-187,199-203, ConvDiscriminator pre_conv :397-404).
+ * x[N,H,W,Cin] (pixel stride ldpix_x >= Cin), w[Cout,Cin,KH,KW] (reference layout),
+ * y[N,Ho,Wo,Cout] (pixel stride ldpix_y).  Conv1d: W = KW = 1. */
+int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, int Cin,
+                  const float* w, const float* bias, float* y, long ldpix_y, int Cout,
+                  int KH, int KW, int sh, int sw, int ph, int pw, int dh, int dw,
+                  int act, float slope, void* stream);
+/* dx (+)= conv_transpose(dy) ; stride must be 1 */
+int s2ag_conv_bwd_data(const float* dy, long ldpix_dy, int N, int H, int W, int Cin,
+                       const float* w, float* dx, long ldpix_dx, int Cout,
+                       int KH, int KW, int ph, int pw, int dh, int dw, int accumulate, void* stream);
+/* dw += , db += (db may be NULL) */
+int s2ag_conv_bwd_weight(const float* dy, long ldpix_dy, const float* x, long ldpix_x,
+                         int N, int H, int W, int Cin, float* dw, float* db, int Cout,
+                         int KH, int KW, int sh, int sw, int ph, int pw, int dh, int dwd, void* stream);
+
+/* ---- nn.BatchNorm1d/2d, train and eval, fused with the following activation -----------------
+ * (:19-25,:40-46,:123,:131,:144,:149; tgcn.py:179,188,204).  x is [M,C] (M = all non-channel
+ * positions), per-column statistics.  param_map (int32[C], may be NULL = identity) gives the
+ * parameter index of each column and col_map (int32[C], may be NULL) the OUTPUT column, which
+ * is how AffEncoder's view/permute regrouping (:155-171) is folded in.
+ *   y[m, col_map[c]] = act( (x[m,c]-mean)/sqrt(var+eps)*gamma[pm[c]] + beta[pm[c]] + add[m, col_map[c]] )
+ * training != 0: batch statistics (biased var), running stats updated with `momentum`
+ * (unbiased var), save_mean/save_invstd[C] written for the backward pass.
+ * ws: double[2*C] scratch. */
+int s2ag_bn_fwd(const float* x, long ldx, int M, int C, const float* gamma, const float* beta,
+                const int32_t* param_map, float* running_mean, float* running_var,
+                int training, float momentum, float eps,
+                const float* add, long ldadd, float* y, long ldy, const int32_t* col_map,
+                int act, float slope, float* save_mean, float* save_invstd, double* ws, void* stream);
+/* dx = BN'(dy * act'(y)); dgamma += ; dbeta += ; dadd (may be NULL) = dy * act'(y).
+ * ws: double[2*C] scratch. */
+int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy, const int32_t* col_map,
+                const float* x, long ldx, int M, int C, const float* gamma, const int32_t* param_map,
+                const float* save_mean, const float* save_invstd, int training, int act, float slope,
+                float* dx, long lddx, float* dgamma, float* dbeta, float* dadd, long lddadd,
+                double* ws, void* stream);
+
+/* ---- ST-GCN adjacency contraction (tgcn.py:67-69: einsum 'nkctv,kvw->nctw') -----------------
+ * x[M, V, K*C] (channel index k*C + c), A[K,V,V], y[M, V, C]:  y[m,w,c] = sum_{k,v} x[m,v,k*C+c] A[k,v,w] */
+int s2ag_graph_fwd(const float* x, const float* A, float* y, int M, int V, int K, int C, void* stream);
+int s2ag_graph_bwd(const float* dy, const float* A, float* dx, int M, int V, int K, int C, void* stream);
+
+/* ---- weight_norm + causal dilated TemporalBlock (net/tcn.py:16-46) ---------------------------
+ * weight_norm (old style, dim=0): w[co] = g[co] * v[co] / ||v[co]||.  v is [Co,Ci,k] (reference
+ * layout); the effective weight is emitted TAP-MAJOR as w[Co][k][Ci] so that a tap is a
+ * contiguous K-slab for the conv-as-GEMM. norm[Co] is saved for the backward. */
+int s2ag_weight_norm_fwd(const float* v, const float* g, float* w, float* norm, int Co, int Ci, int k,
+                         void* stream);
+/* dv += , dg += from dw[Co][k][Ci] */
+int s2ag_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* norm,
+                         float* dv, float* dg, int Co, int Ci, int k, void* stream);
+/* One residual block over x[B,T,C] (channels-last), kernel size 2, dilation d:
+ *   y1 = drop(relu(W1[:,1] x[t] + W1[:,0] x[t-d] + b1)); y2 = drop(relu(conv(y1; W2) + b2));
+ *   out = relu(y2 + x).   The chomped columns are never computed.  y1,y2 saved for backward. */
+int s2ag_tcn_block_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                       float* y1, float* y2, float* out, int B, int T, int C, int dilation,
+                       float p_drop, uint64_t seed, void* stream);
+/* dx = d(out)/d(x); dw1,dw2 [C][2][C] +=, db1,db2 += ; ws: float[2*B*T*C] scratch */
+int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const float* y2, const float* out,
+                       const float* w1, const float* w2, float* dx, float* dw1, float* db1, float* dw2,
+                       float* db2, float* ws, int B, int T, int C, int dilation, float p_drop, void* stream);
+
+/* ---- nn.Embedding (+ nn.Dropout) (:70-73,:88; :470-472) ------------------------------------- */
+int s2ag_embedding_fwd(const int64_t* idx, const float* table, float* out, long ldo, long n, int D, long V,
+                       float p_drop, uint64_t seed, void* stream);
+int s2ag_embedding_bwd(const int64_t* idx, const float* dout, long ldo, float* dtable, long n, int D, long V,
+                       float p_drop, uint64_t seed, void* stream);
+
+/* ---- nn.GRU, one bidirectional layer (:480-481,:281-282,:558-560) ---------------------------
+ * x[B,T,In] (row stride ldx), weights in the reference layout, gate order r,z,n, h0 = 0.
+ * out[B,T,2H] = [forward | reverse].  gi_ws: float[B*T*6H] scratch.  gates (may be NULL when no
+ * backward will follow): float[B*T*2*4*H] receives r,z,n and (W_hn h + b_hn) per (b,t,dir). */
+int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const float* w_ih_r,
+                       const float* b_ih_f, const float* b_ih_r, const float* w_hh_f, const float* w_hh_r,
+                       const float* b_hh_f, const float* b_hh_r, float* gi_ws, float* out, float* gates,
+                       int B, int T, int In, int H, void* stream);
+/* dout[B,T,*]: gradient of the layer output; direction `d` reads columns d*dir_stride .. +H of a
+ * row of stride lddout (dir_stride = H normally; 0 when both halves share the gradient of their
+ * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += .
+ * ws: float[B*T*6H (dgi) + B*T*6H (dgh) + 4*B*H (dh ping-pong)] */
+int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride, const float* x, long ldx,
+                       const float* out, const float* gates,
+                       const float* w_ih_f, const float* w_ih_r, const float* w_hh_f, const float* w_hh_r,
+                       float* dx, long lddx, float* dw_ih_f, float* dw_ih_r, float* db_ih_f, float* db_ih_r,
+                       float* dw_hh_f, float* dw_hh_r, float* db_hh_f, float* db_hh_r, float* ws,
+                       int B, int T, int In, int H, void* stream);
+
+/* ---- speaker style vector (:513-516, :536-539; net/embedding_net.py:10-13) -------------------
+ * z = mu + eps * exp(0.5*logvar); z[B,Z] is also tiled over T into dst[B,T,ld] columns [off, off+Z) */
+int s2ag_reparam_tile_fwd(const float* mu, const float* logvar, const float* eps, float* z,
+                          float* dst, long ld, int off, int B, int T, int Z, void* stream);
+/* dz_total = dz (may be NULL) + sum_t ddst[b,t,off:off+Z]; dmu = dz_total; dlogvar = dz_total*eps*0.5*exp(0.5 logvar) */
+int s2ag_reparam_tile_bwd(const float* ddst, long ld, int off, const float* dz, const float* logvar,
+                          const float* eps, float* dmu, float* dlogvar, int B, int T, int Z, void* stream);
+
+/* ---- discriminator head (:579-585): sigmoid(Linear_T(Linear_H(fwd+rev))) ---------------------
+ * g[B,T,2H]; lin1[B,T] saved; out[B] */
+int s2ag_dhead_fwd(const float* g, const float* w1, const float* b1, const float* w2, const float* b2,
+                   float* lin1, float* out, int B, int T, int H, void* stream);
+/* dg[B,T,2H] (both halves get the same gradient); dw1[H] += , db1[1] +=, dw2[T] +=, db2[1] += */
+int s2ag_dhead_bwd(const float* dout, const float* out, const float* g, const float* lin1,
+                   const float* w1, const float* w2, float* dg, float* dw1, float* db1, float* dw2,
+                   float* db2, int B, int T, int H, void* stream);
+
+/* ---- losses (processor_v2.py:811, 893-937, 956) ---------------------------------------------
+ * D step: loss[0] = -mean(log(real+1e-8) + log(1-fake+1e-8)); d_real, d_fake [B] gradients */
+int s2ag_dis_loss(const float* d_real, const float* d_fake, float* loss, float* g_real, float* g_fake,
+                  int B, void* stream);
+/* G step.  out,tgt,out_rand [B,TP]; z,z_rand,mu,logvar [B,Z]; dis_out [B] (may be NULL: warm-up).
+ * losses[0..4] = huber, gen, kld, div_reg, total (weights w_* applied only in total).
+ * Gradients of `total`: g_out[B,TP], g_dis[B], g_mu[B,Z], g_logvar[B,Z]. */
+int s2ag_gen_loss(const float* out, const float* tgt, const float* out_rand, const float* z,
+                  const float* z_rand, const float* mu, const float* logvar, const float* dis_out,
+                  float w_huber, float w_kld, float w_div, float w_gan,
+                  float* losses, float* g_out, float* g_dis, float* g_mu, float* g_logvar,
+                  int B, int TP, int Z, void* stream);
+/* dst[0] = mean |a - b| over n elements */
+int s2ag_l1_mean(const float* a, const float* b, float* dst, long n, void* stream);
+
+/* ---- optim.Adam over a flat parameter buffer (processor_v2.py:215-220) -----------------------
+ * step_count: device int32, incremented by this call BEFORE use (bias correction reads it on
+ * device so that a captured CUDA graph replays correctly). grad_scale multiplies g (1/world). */
+int s2ag_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, int32_t* step_count, void* stream);
+
+/* ---- attention + softmax over time (net/ser_att_conv_rnn_v2.py:16-34; named off-path) --------
+ * x[N,T,Hd]; v = sigmoid(x W1^T + b1) [A]; e = v . w2 + b2; alpha = softmax_t(e); out[n] = sum_t alpha x */
+int s2ag_attention_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                       float* out, float* alpha, int N, int T, int Hd, int A, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,23 @@
+// Library-level entry points: version, error string.
+#include "s2ag.h"
+#include "common.cuh"
+#include <cstdarg>
+
+static thread_local char g_err[512] = "";
+
+void s2ag_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int s2ag_version(void) { return 100; }
+extern "C" const char* s2ag_last_error(void) { return g_err; }
+extern "C" int s2ag_is_device_build(void) {
+#ifdef S2AG_EMU
+  return 0;
+#else
+  return 1;
+#endif
+}

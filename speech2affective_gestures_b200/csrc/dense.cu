@@ -1,0 +1,180 @@
+// Linear / Conv (channels-last implicit GEMM) forward and backward, plus the small elementwise
+// helpers around them.  Replaces the nn.Linear / nn.Conv1d / nn.Conv2d call sites listed in
+// include/s2ag.h.  All fp32, exact-order-independent up to fp32 summation order.
+#include "s2ag.h"
+#include "gemm_simt.cuh"
+
+using namespace s2ag;
+
+// ------------------------------------------------------------------ column sums (bias grads)
+// db[n] += sum_m dy[m*ld + n]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long ld, float* __restrict__ db,
+                                                     int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + tx;
+  const int mbeg = blockIdx.y * rows_per_block;
+  int mend = mbeg + rows_per_block; if (mend > M) mend = M;
+  float s = 0.f;
+  if (n < N) for (int m = mbeg + ty; m < mend; m += 8) s += __ldg(dy + (long)m * ld + n);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(db + n, t);
+  }
+}
+namespace s2ag {
+void launch_colsum(const float* dy, long ld, float* db, int M, int N, void* stream) {
+  int rpb = 256;
+  dim3 grid(s2ag_cdiv(N, 32), s2ag_cdiv(M, rpb));
+  auto kfn = &colsum_kernel;
+  S2AG_LAUNCH(kfn, grid, 256, 0, stream, dy, ld, db, M, N, rpb);
+}
+}  // namespace s2ag
+
+// ------------------------------------------------------------------ Linear
+extern "C" int s2ag_linear_fwd(const float* x, long ldx, const float* w, const float* bias, float* y, long ldy,
+                               int M, int N, int K, int act, float slope, void* stream) {
+  S2AG_CHECK_ARG(x && w && y && M >= 0 && N > 0 && K > 0 && ldx >= K && ldy >= N);
+  LdPlain<true> a{x, ldx, 1, 0};
+  LdPlain<true> b{w, (long)K, 1, 0};
+  launch_gemm(a, b, make_epi(y, ldy, bias, act, slope, 0), M, N, K, 1, 1, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_linear_bwd_data(const float* dy, long lddy, const float* w, float* dx, long lddx,
+                                    int M, int N, int K, int accumulate, void* stream) {
+  S2AG_CHECK_ARG(dy && w && dx && M >= 0 && N > 0 && K > 0 && lddy >= N && lddx >= K);
+  // dx[m,k] = sum_n dy[m,n] w[n,k]  -> rows m, cols k, contraction n
+  LdPlain<true> a{dy, lddy, 1, 0};
+  LdPlain<false> b{w, 1, (long)K, 0};  // element(row=k, kk=n) = w[n*K + k]
+  launch_gemm(a, b, make_epi(dx, lddx, nullptr, 0, 0.f, accumulate ? 1 : 0), M, K, N, 1, 1, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_linear_bwd_weight(const float* dy, long lddy, const float* x, long ldx, float* dw, float* db,
+                                      int M, int N, int K, void* stream) {
+  S2AG_CHECK_ARG(dy && x && dw && M >= 0 && N > 0 && K > 0 && lddy >= N && ldx >= K);
+  if (M == 0) return S2AG_OK;
+  // dw[n,k] += sum_m dy[m,n] x[m,k]  -> rows n, cols k, contraction m
+  LdPlain<false> a{dy, 1, lddy, 0};
+  LdPlain<false> b{x, 1, ldx, 0};
+  int sk = pick_splitk(N, K, M, 1);
+  launch_gemm(a, b, make_epi(dw, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), N, K, M, 1, sk, stream);
+  if (db) launch_colsum(dy, lddy, db, M, N, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+__global__ void act_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ y, long ldy,
+                               float* __restrict__ dpre, long ldd, int M, int N, int act, float slope) {
+  long total = (long)M * N;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int m = (int)(i / N), n = (int)(i % N);
+    dpre[(long)m * ldd + n] = dy[(long)m * lddy + n] * s2ag_act_grad_from_out(y[(long)m * ldy + n], act, slope);
+  }
+}
+extern "C" int s2ag_act_bwd(const float* dy, long lddy, const float* y, long ldy, float* dpre, long ldd,
+                            int M, int N, int act, float slope, void* stream) {
+  S2AG_CHECK_ARG(dy && y && dpre && M >= 0 && N > 0);
+  long total = (long)M * N;
+  if (total == 0) return S2AG_OK;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  auto kfn = &act_bwd_kernel;
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, dy, lddy, y, ldy, dpre, ldd, M, N, act, slope);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+__global__ void add_halves_kernel(const float* __restrict__ x, float* __restrict__ y, long M, int H) {
+  long total = M * H;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long m = i / H; int h = (int)(i % H);
+    y[i] = x[m * 2 * H + h] + x[m * 2 * H + H + h];
+  }
+}
+extern "C" int s2ag_add_halves(const float* x, float* y, int M, int H, void* stream) {
+  S2AG_CHECK_ARG(x && y && M >= 0 && H > 0);
+  long total = (long)M * H;
+  if (total == 0) return S2AG_OK;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  auto kfn = &add_halves_kernel;
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, x, y, (long)M, H);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float p,
+                               unsigned long long seed) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = x[i] * s2ag_dropout_scale(seed, (unsigned long long)i, p);
+}
+extern "C" int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, void* stream) {
+  S2AG_CHECK_ARG(x && y && n >= 0 && p >= 0.f && p < 1.f);
+  if (n == 0) return S2AG_OK;
+  int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  auto kfn = &dropout_kernel;
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, x, y, n, p, (unsigned long long)seed);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+// ------------------------------------------------------------------ Conv (channels-last implicit GEMM)
+static inline int conv_out(int L, int k, int s, int p, int d) { return (L + 2 * p - d * (k - 1) - 1) / s + 1; }
+
+extern "C" int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, int Cin,
+                             const float* w, const float* bias, float* y, long ldpix_y, int Cout,
+                             int KH, int KW, int sh, int sw, int ph, int pw, int dh, int dw,
+                             int act, float slope, void* stream) {
+  S2AG_CHECK_ARG(x && w && y && N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0);
+  S2AG_CHECK_ARG(sh > 0 && sw > 0 && dh > 0 && dw > 0 && ldpix_x >= Cin && ldpix_y >= Cout);
+  int Ho = conv_out(H, KH, sh, ph, dh), Wo = conv_out(W, KW, sw, pw, dw);
+  S2AG_CHECK_ARG(Ho > 0 && Wo > 0);
+  LdConv<ORDER_CKK> a{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dw, +1, -ph, -pw, ldpix_x};
+  int K = Cin * KH * KW;
+  LdPlain<true> b{w, (long)K, 1, 0};
+  launch_gemm(a, b, make_epi(y, ldpix_y, bias, act, slope, 0), N * Ho * Wo, Cout, K, 1, 1, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_conv_bwd_data(const float* dy, long ldpix_dy, int N, int H, int W, int Cin,
+                                  const float* w, float* dx, long ldpix_dx, int Cout,
+                                  int KH, int KW, int ph, int pw, int dh, int dw, int accumulate, void* stream) {
+  S2AG_CHECK_ARG(dy && w && dx && N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+  int Ho = conv_out(H, KH, 1, ph, dh), Wo = conv_out(W, KW, 1, pw, dw);
+  S2AG_CHECK_ARG(Ho > 0 && Wo > 0 && ldpix_dy >= Cout && ldpix_dx >= Cin);
+  // dx[n,hi,wi,c] = sum_{co,kh,kw} dy[n, hi+ph-kh*dh, wi+pw-kw*dw, co] * w[co,c,kh,kw]
+  LdConv<ORDER_CKK> a{dy, Ho, Wo, Cout, H, W, KH, KW, 1, 1, dh, dw, -1, ph, pw, ldpix_dy};
+  int KK = KH * KW;
+  LdWdgrad<ORDER_CKK> b{w, Cout, KK, (long)Cin * KK, (long)KK, 1};
+  launch_gemm(a, b, make_epi(dx, ldpix_dx, nullptr, 0, 0.f, accumulate ? 1 : 0), N * H * W, Cin, Cout * KK, 1, 1,
+              stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_conv_bwd_weight(const float* dy, long ldpix_dy, const float* x, long ldpix_x,
+                                    int N, int H, int W, int Cin, float* dw, float* db, int Cout,
+                                    int KH, int KW, int sh, int sw, int ph, int pw, int dh, int dwd, void* stream) {
+  S2AG_CHECK_ARG(dy && x && dw && N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+  int Ho = conv_out(H, KH, sh, ph, dh), Wo = conv_out(W, KW, sw, pw, dwd);
+  S2AG_CHECK_ARG(Ho > 0 && Wo > 0 && ldpix_dy >= Cout && ldpix_x >= Cin);
+  int Mrows = N * Ho * Wo;
+  if (Mrows == 0) return S2AG_OK;
+  int K = Cin * KH * KW;
+  // dw[co, kcol] += sum_row dy[row, co] * im2col(x)[row, kcol]
+  LdPlain<false> a{dy, 1, ldpix_dy, 0};
+  LdT<LdConv<ORDER_CKK>> b{LdConv<ORDER_CKK>{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dwd, +1, -ph, -pw, ldpix_x}};
+  int sk = pick_splitk(Cout, K, Mrows, 1);
+  launch_gemm(a, b, make_epi(dw, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), Cout, K, Mrows, 1, sk, stream);
+  if (db) launch_colsum(dy, ldpix_dy, db, Mrows, Cout, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
