@@ -52,7 +52,11 @@ int s2ag_act_bwd(const float* dy, long lddy, const float* y, long ldy, float* dp
 int s2ag_add_halves(const float* x, float* y, int M, int H, void* stream);
 /* y = x * mask(seed)/(1-p) (nn.Dropout / nn.GRU inter-layer dropout); stateless counter RNG so
  * the backward call regenerates the mask from the same seed. In-place allowed. */
-int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, void* stream);
+int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+/* seed_dev[0] += inc.  Every dropout-bearing call takes (seed, seed_dev): the effective seed is
+ * seed + *seed_dev (seed_dev may be NULL), so a captured CUDA graph draws fresh masks on every
+ * replay once the step nonce is advanced inside the graph. */
+int s2ag_seed_advance(uint64_t* seed_dev, uint64_t inc, void* stream);
 
 /* ---- nn.Conv1d / nn.Conv2d over channels-last activations -----------------------------------
  * (WavEncoder :17-27, MFCCEncoder :39-45, AffEncoder :146-150, STGraphConv tgcn.py:64-68,
@@ -113,7 +117,7 @@ int s2ag_weight_norm_bwd(const float* dw, const float* v, const float* g, const 
  *   out = relu(y2 + x).   The chomped columns are never computed.  y1,y2 saved for backward. */
 int s2ag_tcn_block_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                        float* y1, float* y2, float* out, int B, int T, int C, int dilation,
-                       float p_drop, uint64_t seed, void* stream);
+                       float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* dx = d(out)/d(x); dw1,dw2 [C][2][C] +=, db1,db2 += ; ws: float[2*B*T*C] scratch */
 int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const float* y2, const float* out,
                        const float* w1, const float* w2, float* dx, float* dw1, float* db1, float* dw2,
@@ -121,9 +125,9 @@ int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const
 
 /* ---- nn.Embedding (+ nn.Dropout) (:70-73,:88; :470-472) ------------------------------------- */
 int s2ag_embedding_fwd(const int64_t* idx, const float* table, float* out, long ldo, long n, int D, long V,
-                       float p_drop, uint64_t seed, void* stream);
+                       float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
 int s2ag_embedding_bwd(const int64_t* idx, const float* dout, long ldo, float* dtable, long n, int D, long V,
-                       float p_drop, uint64_t seed, void* stream);
+                       float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
 
 /* ---- nn.GRU, one bidirectional layer (:480-481,:281-282,:558-560) ---------------------------
  * x[B,T,In] (row stride ldx), weights in the reference layout, gate order r,z,n, h0 = 0.

@@ -111,16 +111,29 @@ extern "C" int s2ag_add_halves(const float* x, float* y, int M, int H, void* str
 }
 
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float p,
-                               unsigned long long seed) {
+                               unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += seed_dev[0];
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = x[i] * s2ag_dropout_scale(seed, (unsigned long long)i, p);
 }
-extern "C" int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, void* stream) {
+extern "C" int s2ag_dropout(const float* x, float* y, long n, float p, uint64_t seed, const uint64_t* seed_dev,
+                            void* stream) {
   S2AG_CHECK_ARG(x && y && n >= 0 && p >= 0.f && p < 1.f);
   if (n == 0) return S2AG_OK;
   int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   auto kfn = &dropout_kernel;
-  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, x, y, n, p, (unsigned long long)seed);
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, x, y, n, p, (unsigned long long)seed, (const unsigned long long*)seed_dev);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+__global__ void seed_advance_kernel(unsigned long long* s, unsigned long long inc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) s[0] += inc;
+}
+extern "C" int s2ag_seed_advance(uint64_t* seed_dev, uint64_t inc, void* stream) {
+  S2AG_CHECK_ARG(seed_dev);
+  auto kfn = &seed_advance_kernel;
+  S2AG_LAUNCH(kfn, 1, 32, 0, stream, (unsigned long long*)seed_dev, (unsigned long long)inc);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }

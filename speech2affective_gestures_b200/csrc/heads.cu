@@ -1,0 +1,351 @@
+// Small fused kernels around the dense core: speaker re-parametrisation, discriminator head,
+// GAN losses (value + gradient in one pass), L1 metric, Adam, and the sigmoid-MLP attention +
+// softmax-over-time block.  All latency/HBM-bound, SIMT with warp-shuffle reductions.
+// Reference: net/embedding_net.py:10-13; net/multimodal_context_net_v2.py:536-539,579-585;
+// processor_v2.py:811,893-937,956,215-220; net/ser_att_conv_rnn_v2.py:30-34.
+#include "s2ag.h"
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 32 floats */) {
+  // all threads must call; returns the block total to every thread
+  const int lane = threadIdx.x % 32, wid = threadIdx.x / 32, nw = (blockDim.x + 31) / 32;
+  v = s2ag_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// ---------------------------------------------------------------- reparametrise + tile
+__global__ void reparam_tile_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                        const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ dst,
+                                        long ld, int off, int B, int T, int Z) {
+  const long total = (long)B * T * Z;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Z); const int t = (int)((i / Z) % T); const int b = (int)(i / ((long)Z * T));
+    const float v = mu[b * Z + k] + eps[b * Z + k] * expf(0.5f * logvar[b * Z + k]);
+    if (t == 0) z[b * Z + k] = v;
+    if (dst) dst[((long)b * T + t) * ld + off + k] = v;
+  }
+}
+__global__ void reparam_tile_bwd_kernel(const float* __restrict__ ddst, long ld, int off, const float* __restrict__ dz,
+                                        const float* __restrict__ logvar, const float* __restrict__ eps,
+                                        float* __restrict__ dmu, float* __restrict__ dlogvar, int B, int T, int Z) {
+  const int total = B * Z;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Z, b = i / Z;
+    float s = dz ? dz[i] : 0.f;
+    if (ddst) for (int t = 0; t < T; ++t) s += ddst[((long)b * T + t) * ld + off + k];
+    dmu[i] = s;
+    dlogvar[i] = s * eps[i] * 0.5f * expf(0.5f * logvar[i]);
+  }
+}
+
+// ---------------------------------------------------------------- discriminator head
+// one block (128 threads) per clip
+__global__ void __launch_bounds__(128) dhead_fwd_kernel(const float* __restrict__ g, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ lin1,
+                                                        float* __restrict__ out, int T, int H) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, lane = threadIdx.x % 32, wid = threadIdx.x / 32;
+  float part = 0.f;  // this warp's share of sum_t lin1*w2
+  for (int t = wid; t < T; t += 4) {
+    const float* row = g + ((long)b * T + t) * 2 * H;
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s = fmaf(row[j] + row[H + j], w1[j], s);
+    s = s2ag_warp_sum(s) + b1[0];
+    if (lane == 0) { lin1[(long)b * T + t] = s; part = fmaf(s, w2[t], part); }
+  }
+  const float tot = block_sum(part, red);
+  if (threadIdx.x == 0) out[b] = s2ag_sigmoid(tot + b2[0]);
+}
+__global__ void __launch_bounds__(128) dhead_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                        const float* __restrict__ g, const float* __restrict__ lin1,
+                                                        const float* __restrict__ w1, const float* __restrict__ w2,
+                                                        float* __restrict__ dg, float* __restrict__ dw1,
+                                                        float* __restrict__ db1, float* __restrict__ dw2,
+                                                        float* __restrict__ db2, int T, int H) {
+  const int b = blockIdx.x;
+  const float o = out[b];
+  const float dpre = dout[b] * o * (1.f - o);
+  // dlin1[t] = dpre * w2[t]
+  for (int t = threadIdx.x; t < T; t += 128) atomicAdd(dw2 + t, dpre * lin1[(long)b * T + t]);
+  if (threadIdx.x == 0) {
+    atomicAdd(db2, dpre);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += w2[t];
+    atomicAdd(db1, dpre * s);
+  }
+  for (int j = threadIdx.x; j < H; j += 128) {
+    float acc = 0.f;
+    const float wj = w1[j];
+    for (int t = 0; t < T; ++t) {
+      const float dl = dpre * w2[t];
+      const long r = ((long)b * T + t) * 2 * H;
+      acc = fmaf(dl, g[r + j] + g[r + H + j], acc);
+      if (dg) { dg[r + j] = dl * wj; dg[r + H + j] = dl * wj; }
+    }
+    atomicAdd(dw1 + j, acc);
+  }
+}
+
+// ---------------------------------------------------------------- losses
+__global__ void __launch_bounds__(256) dis_loss_kernel(const float* __restrict__ dr, const float* __restrict__ df,
+                                                       float* __restrict__ loss, float* __restrict__ gr,
+                                                       float* __restrict__ gf, int B) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv = 1.f / (float)B;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float r = dr[b] + 1e-8f, f = 1.f - df[b] + 1e-8f;
+    s += logf(r) + logf(f);
+    if (gr) gr[b] = -inv / r;
+    if (gf) gf[b] = inv / f;
+  }
+  const float tot = block_sum(s, red);
+  if (threadIdx.x == 0) loss[0] = -tot * inv;
+}
+
+__device__ __forceinline__ float sl1(float d) { const float a = fabsf(d); return a < 1.f ? 0.5f * d * d : a - 0.5f; }
+__device__ __forceinline__ float sl1_grad(float d) { return fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f); }
+
+// one block per clip; losses[] pre-zeroed
+__global__ void __launch_bounds__(256) gen_loss_kernel(
+    const float* __restrict__ out, const float* __restrict__ tgt, const float* __restrict__ out_rand,
+    const float* __restrict__ z, const float* __restrict__ z_rand, const float* __restrict__ mu,
+    const float* __restrict__ logvar, const float* __restrict__ dis_out, float w_huber, float w_kld, float w_div,
+    float w_gan, float* __restrict__ losses, float* __restrict__ g_out, float* __restrict__ g_dis,
+    float* __restrict__ g_mu, float* __restrict__ g_logvar, int B, int TP, int Z) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* o = out + (long)b * TP;
+  const float* tg = tgt + (long)b * TP;
+  const float* orr = out_rand ? out_rand + (long)b * TP : nullptr;
+  const float invB = 1.f / (float)B, invN = 1.f / ((float)B * (float)TP);
+  float hs = 0.f, ps = 0.f;
+  for (int i = threadIdx.x; i < TP; i += 256) {
+    const float v = o[i];
+    hs += sl1((v - tg[i]) * 10.f);                      // beta = 0.1
+    if (orr) ps += sl1((v - orr[i]) * 20.f);            // beta = 0.05
+  }
+  const float hub = block_sum(hs, red) * 0.1f;
+  const float pose_l1 = block_sum(ps, red) * 0.05f;
+  float zs = 0.f, ks = 0.f;
+  if (orr)
+    for (int i = threadIdx.x; i < Z; i += 256) {
+      zs += fabsf(z[b * Z + i] - z_rand[b * Z + i]);
+      const float m = mu[b * Z + i], lv = logvar[b * Z + i];
+      ks += 1.f + lv - m * m - expf(lv);
+      if (g_mu) g_mu[b * Z + i] = w_kld * m / ((float)B * (float)Z);
+      if (g_logvar) g_logvar[b * Z + i] = w_kld * (-0.5f) * (1.f - expf(lv)) / ((float)B * (float)Z);
+    }
+  const float z_l1 = block_sum(zs, red) / (float)Z;
+  const float kld_part = -0.5f * block_sum(ks, red) / ((float)B * (float)Z);
+  float div_b = 0.f, div_coef = 0.f;
+  if (orr) {
+    const float den = z_l1 + 1.0e-5f;
+    div_b = -pose_l1 / den;
+    if (div_b < -1000.f) { div_b = -1000.f; div_coef = 0.f; } else div_coef = -1.f / den;
+  }
+  float gen_b = 0.f;
+  if (dis_out) {
+    const float d = dis_out[b] + 1e-8f;
+    gen_b = -logf(d);
+    if (threadIdx.x == 0 && g_dis) g_dis[b] = w_gan * (-invB / d);
+  }
+  if (g_out)
+    for (int i = threadIdx.x; i < TP; i += 256) {
+      const float v = o[i];
+      float gr = w_huber * sl1_grad((v - tg[i]) * 10.f) * invN;
+      if (orr) gr += w_div * invB * div_coef * sl1_grad((v - orr[i]) * 20.f);
+      g_out[(long)b * TP + i] = gr;
+    }
+  if (threadIdx.x == 0) {
+    const float h = hub * invN, ge = gen_b * invB, dv = div_b * invB;
+    atomicAdd(losses + 0, h);
+    atomicAdd(losses + 1, ge);
+    atomicAdd(losses + 2, kld_part);
+    atomicAdd(losses + 3, dv);
+    atomicAdd(losses + 4, w_huber * h + w_gan * ge + w_kld * kld_part + w_div * dv);
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_mean_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      float* __restrict__ dst, long n) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    s += fabsf(a[i] - b[i]);
+  const float tot = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(dst, tot / (float)n);
+}
+
+// ---------------------------------------------------------------- Adam
+__global__ void counter_inc_kernel(int32_t* c) { if (threadIdx.x == 0 && blockIdx.x == 0) c[0] += 1; }
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long n, float lr,
+                                                   float beta1, float beta2, float eps, float grad_scale,
+                                                   const int32_t* __restrict__ step_count) {
+  const float t = (float)step_count[0];
+  const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
+// ---------------------------------------------------------------- attention + softmax over time
+// one block (256 threads) per sequence; dynamic smem: e[T]
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, float* __restrict__ out,
+                                                            float* __restrict__ alpha, int T, int Hd, int A) {
+  S2AG_DYN_SMEM(float, e);
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float* xs = x + (long)n * T * Hd;
+  float lmax = -3.0e38f;
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const float* xr = xs + (long)t * Hd;
+    float s = b2[0];
+    for (int a = 0; a < A; ++a) {
+      float d = b1[a];
+      for (int h = 0; h < Hd; ++h) d = fmaf(xr[h], __ldg(w1 + a * Hd + h), d);
+      s = fmaf(s2ag_sigmoid(d), w2[a], s);
+    }
+    e[t] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  // block max
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  __syncthreads();
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = lmax;
+  __syncthreads();
+  float mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  float ls = 0.f;
+  for (int t = threadIdx.x; t < T; t += 256) { const float p = expf(e[t] - mx); e[t] = p; ls += p; }
+  const float denom = block_sum(ls, red);
+  for (int t = threadIdx.x; t < T; t += 256) { const float a = e[t] / denom; e[t] = a; if (alpha) alpha[(long)n * T + t] = a; }
+  __syncthreads();
+  for (int h = threadIdx.x; h < Hd; h += 256) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s = fmaf(e[t], xs[(long)t * Hd + h], s);
+    out[(long)n * Hd + h] = s;
+  }
+}
+
+static inline int ew_blocks(long total) {
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  return blocks;
+}
+
+}  // namespace
+
+extern "C" int s2ag_reparam_tile_fwd(const float* mu, const float* logvar, const float* eps, float* z,
+                                     float* dst, long ld, int off, int B, int T, int Z, void* stream) {
+  S2AG_CHECK_ARG(mu && logvar && eps && z && B >= 0 && T > 0 && Z > 0);
+  if (B == 0) return S2AG_OK;
+  auto kfn = &reparam_tile_fwd_kernel;
+  S2AG_LAUNCH(kfn, ew_blocks((long)B * T * Z), 256, 0, stream, mu, logvar, eps, z, dst, ld, off, B, T, Z);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+extern "C" int s2ag_reparam_tile_bwd(const float* ddst, long ld, int off, const float* dz, const float* logvar,
+                                     const float* eps, float* dmu, float* dlogvar, int B, int T, int Z, void* stream) {
+  S2AG_CHECK_ARG(logvar && eps && dmu && dlogvar && B >= 0 && T > 0 && Z > 0);
+  if (B == 0) return S2AG_OK;
+  auto kfn = &reparam_tile_bwd_kernel;
+  S2AG_LAUNCH(kfn, ew_blocks((long)B * Z), 256, 0, stream, ddst, ld, off, dz, logvar, eps, dmu, dlogvar, B, T, Z);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_dhead_fwd(const float* g, const float* w1, const float* b1, const float* w2, const float* b2,
+                              float* lin1, float* out, int B, int T, int H, void* stream) {
+  S2AG_CHECK_ARG(g && w1 && b1 && w2 && b2 && lin1 && out && B >= 0 && T > 0 && H > 0);
+  if (B == 0) return S2AG_OK;
+  auto kfn = &dhead_fwd_kernel;
+  S2AG_LAUNCH(kfn, B, 128, 0, stream, g, w1, b1, w2, b2, lin1, out, T, H);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+extern "C" int s2ag_dhead_bwd(const float* dout, const float* out, const float* g, const float* lin1,
+                              const float* w1, const float* w2, float* dg, float* dw1, float* db1, float* dw2,
+                              float* db2, int B, int T, int H, void* stream) {
+  S2AG_CHECK_ARG(dout && out && g && lin1 && w1 && w2 && dw1 && db1 && dw2 && db2 && B >= 0 && T > 0 && H > 0);
+  if (B == 0) return S2AG_OK;
+  auto kfn = &dhead_bwd_kernel;
+  S2AG_LAUNCH(kfn, B, 128, 0, stream, dout, out, g, lin1, w1, w2, dg, dw1, db1, dw2, db2, T, H);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_dis_loss(const float* d_real, const float* d_fake, float* loss, float* g_real, float* g_fake,
+                             int B, void* stream) {
+  S2AG_CHECK_ARG(d_real && d_fake && loss && B > 0);
+  auto kfn = &dis_loss_kernel;
+  S2AG_LAUNCH(kfn, 1, 256, 0, stream, d_real, d_fake, loss, g_real, g_fake, B);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_gen_loss(const float* out, const float* tgt, const float* out_rand, const float* z,
+                             const float* z_rand, const float* mu, const float* logvar, const float* dis_out,
+                             float w_huber, float w_kld, float w_div, float w_gan,
+                             float* losses, float* g_out, float* g_dis, float* g_mu, float* g_logvar,
+                             int B, int TP, int Z, void* stream) {
+  S2AG_CHECK_ARG(out && tgt && losses && B > 0 && TP > 0);
+  S2AG_CHECK_ARG(!out_rand || (z && z_rand && mu && logvar && Z > 0));
+  cudaMemsetAsync(losses, 0, 5 * sizeof(float), (cudaStream_t)stream);
+  auto kfn = &gen_loss_kernel;
+  S2AG_LAUNCH(kfn, B, 256, 0, stream, out, tgt, out_rand, z, z_rand, mu, logvar, dis_out, w_huber, w_kld, w_div, w_gan,
+              losses, g_out, g_dis, g_mu, g_logvar, B, TP, Z);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_l1_mean(const float* a, const float* b, float* dst, long n, void* stream) {
+  S2AG_CHECK_ARG(a && b && dst && n > 0);
+  cudaMemsetAsync(dst, 0, sizeof(float), (cudaStream_t)stream);
+  int blocks = ew_blocks(n); if (blocks > 148) blocks = 148;
+  auto kfn = &l1_mean_kernel;
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, a, b, dst, n);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                              float beta2, float eps, float grad_scale, int32_t* step_count, void* stream) {
+  S2AG_CHECK_ARG(p && g && m && v && step_count && n >= 0);
+  auto k0 = &counter_inc_kernel;
+  S2AG_LAUNCH(k0, 1, 32, 0, stream, step_count);
+  if (n > 0) {
+    auto kfn = &adam_kernel;
+    S2AG_LAUNCH(kfn, ew_blocks(n), 256, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, grad_scale,
+                (const int32_t*)step_count);
+  }
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_attention_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  float* out, float* alpha, int N, int T, int Hd, int A, void* stream) {
+  S2AG_CHECK_ARG(x && w1 && b1 && w2 && b2 && out && N >= 0 && T > 0 && Hd > 0 && A > 0 && T <= 8192);
+  if (N == 0) return S2AG_OK;
+  auto kfn = &attention_fwd_kernel;
+  S2AG_LAUNCH(kfn, N, 256, T * sizeof(float), stream, x, w1, b1, w2, b2, out, alpha, T, Hd, A);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}

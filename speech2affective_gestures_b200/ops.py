@@ -1,0 +1,672 @@
+"""Host-side operator layer: torch.autograd.Function wrappers over the C ABI (include/s2ag.h).
+
+PyTorch is used here for device memory (torch.empty), stream handles and the autograd tape; every
+FLOP of the hot path is executed by libs2ag_b200.so.  There is no fallback: tensors must live on
+a CUDA device (or, in tests/emu only, on the CPU with the kernel-logic emulator injected).
+
+Layout convention (see include/s2ag.h): activations are channels-last; parameter gradients are
+ACCUMULATED by the kernels straight into `param.grad` (which the network modules alias onto one
+flat buffer per network), so the backward functions return None for parameters.
+"""
+import ctypes
+import itertools
+
+import torch
+
+from . import _C
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+_seed_counter = itertools.count(1)
+_base_seed = 0x5A2A6000
+_seed_dev = {}
+
+
+def manual_seed(seed):
+    """Re-seed the dropout stream of this process (mirrors torch.manual_seed at processor_v2.py:37)."""
+    global _seed_counter, _base_seed
+    _base_seed = int(seed) & 0xFFFFFFFF
+    _seed_counter = itertools.count(1)
+
+
+def next_seed():
+    return (_base_seed << 20) + next(_seed_counter) * 0x9E3779B1
+
+
+def seed_nonce(device):
+    """Device-resident uint64 added to every dropout seed; advanced once per training step so
+    CUDA-graph replays draw fresh masks."""
+    key = str(device)
+    if key not in _seed_dev:
+        _seed_dev[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _seed_dev[key]
+
+
+def advance_seed_nonce(device, inc=0x100000001B3):
+    t = seed_nonce(device)
+    _C.call("s2ag_seed_advance", _p(t), ctypes.c_uint64(inc), _stream(t))
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    if t.is_cuda:
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
+def _check(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda and not _C.is_emulated():
+            raise _C.S2agError("s2ag ops need CUDA tensors: this path has no CPU fallback")
+        if t.dtype not in (torch.float32, torch.int64, torch.int32, torch.float64):
+            raise _C.S2agError("unsupported dtype %s" % t.dtype)
+
+
+def _rows(t, ncols):
+    """View t as [M, ncols] rows with a uniform row stride (last dim contiguous). -> (tensor, ld)"""
+    if t.shape[-1] != ncols:
+        raise _C.S2agError("expected last dim %d, got %s" % (ncols, tuple(t.shape)))
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    ok = t.stride(-1) == 1 or ncols == 1
+    ld = t.stride(-2) if t.shape[-2] > 1 else max(ncols, t.stride(-2))
+    # outer dims must be expressible as multiples of the row stride
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] > 1 and t.stride(d) != exp:
+            ok = False
+        exp *= t.shape[d]
+    if ld < ncols:
+        ok = False
+    if not ok:
+        t = t.contiguous()
+        ld = ncols
+    return t, ld
+
+
+def col_slice(buf, a, b):
+    """Fresh (non-view) alias of buf[..., a:b] for a contiguous `buf`: producers write their
+    features straight into their column range of the GRU input buffer, and because the alias is
+    not an autograd view of `buf`, each producer's output is an ordinary graph node."""
+    assert buf.is_contiguous()
+    size = tuple(buf.shape[:-1]) + (b - a,)
+    return buf.new_empty(0).set_(buf.untyped_storage(), buf.storage_offset() + a, size, buf.stride())
+
+
+class Out:
+    """Holder that smuggles a pre-allocated destination past autograd's input bookkeeping."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+def _grad_of(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+def _empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------ Linear
+class LinearFn(torch.autograd.Function):
+    """y = act(x @ w.T + b) on the last dim; `out` (optional) is a pre-allocated, possibly
+    column-sliced destination (this is how torch.cat at net/multimodal_context_net_v2.py:526 is
+    avoided).  Reference: nn.Linear call sites listed in include/s2ag.h."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, slope, out):
+        _check(x, w, b)
+        N, K = w.shape
+        xr, ldx = _rows(x, K)
+        M = x.numel() // K
+        y = out.t if out is not None else _empty(x.shape[:-1] + (N,), x)
+        yr, ldy = _rows(y, N)
+        assert yr.data_ptr() == y.data_ptr(), "out must be row-strided"
+        _C.call("s2ag_linear_fwd", _p(xr), ldx, _p(w), _p(b), _p(yr), ldy, M, N, K, act, float(slope), _stream(x))
+        ctx.t = (xr, w, y)
+        ctx.cfg = (act, float(slope), M, N, K, ldx, b)
+        ctx.xshape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, w, y = ctx.t
+        act, slope, M, N, K, ldx, b = ctx.cfg
+        dyr, lddy = _rows(dy, N)
+        st = _stream(dy)
+        if act != ACT_NONE:
+            yr, ldy = _rows(y, N)
+            dpre = _empty((M, N), dy)
+            _C.call("s2ag_act_bwd", _p(dyr), lddy, _p(yr), ldy, _p(dpre), N, M, N, act, slope, st)
+            dyr, lddy = dpre, N
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty(ctx.xshape, dy)
+            _C.call("s2ag_linear_bwd_data", _p(dyr), lddy, _p(w), _p(dx), K, M, N, K, 0, st)
+        if w.requires_grad:
+            db = _grad_of(b) if (b is not None and b.requires_grad) else None
+            _C.call("s2ag_linear_bwd_weight", _p(dyr), lddy, _p(xr), ldx, _p(_grad_of(w)), _p(db), M, N, K, st)
+        return dx, None, None, None, None, None
+
+
+def linear(x, w, b=None, act=ACT_NONE, slope=0.0, out=None):
+    return LinearFn.apply(x, w, b, act, slope, None if out is None else Out(out))
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm helper
+class _BnState:
+    """The per-call record a BN forward leaves for its backward."""
+    __slots__ = ("x", "ldx", "M", "C", "mean", "invstd", "training", "act", "slope", "y", "ldy", "cmap", "pmap")
+
+
+def _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2=None, ldadd=0, cmap=None, pmap=None):
+    """x2/y2: row views. bn: module-like with weight,bias,running_mean,running_var,momentum,eps."""
+    mean = _empty((C,), x2)
+    invstd = _empty((C,), x2)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    _C.call("s2ag_bn_fwd", _p(x2), ldx, M, C, _p(bn.weight), _p(bn.bias), _p(pmap), _p(bn.running_mean),
+            _p(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps), _p(add2), ldadd, _p(y2), ldy,
+            _p(cmap), act, float(slope), _p(mean), _p(invstd), _p(ws), _stream(x2))
+    if training:
+        bn._s2ag_batches = getattr(bn, "_s2ag_batches", 0) + 1
+    s = _BnState()
+    s.x, s.ldx, s.M, s.C, s.mean, s.invstd, s.training = x2, ldx, M, C, mean, invstd, training
+    s.act, s.slope, s.y, s.ldy, s.cmap, s.pmap = act, float(slope), y2, ldy, cmap, pmap
+    return s
+
+
+def _bn_backward(s, bn, dy2, lddy, need_dx=True, dadd2=None, lddadd=0):
+    ws = torch.empty(2 * s.C, dtype=torch.float64, device=dy2.device)
+    dx = _empty((s.M, s.C), dy2) if need_dx else None
+    wg = bn.weight.requires_grad
+    _C.call("s2ag_bn_bwd", _p(dy2), lddy, _p(s.y), s.ldy, _p(s.cmap), _p(s.x), s.ldx, s.M, s.C, _p(bn.weight),
+            _p(s.pmap), _p(s.mean), _p(s.invstd), 1 if s.training else 0, s.act, s.slope, _p(dx), s.C,
+            _p(_grad_of(bn.weight)) if wg else None, _p(_grad_of(bn.bias)) if wg else None, _p(dadd2), lddadd,
+            _p(ws), _stream(dy2))
+    return dx
+
+
+class BnActFn(torch.autograd.Function):
+    """y = act(BN(x) [+ add]) over channels-last x[..., C]; optional column maps (see s2ag_bn_fwd).
+    Reference: nn.BatchNorm1d/2d call sites in include/s2ag.h."""
+
+    @staticmethod
+    def forward(ctx, x, add, gamma, beta, bn, training, act, slope, cmap, pmap, out):
+        _check(x, add)
+        C = x.shape[-1]
+        x2, ldx = _rows(x, C)
+        M = x.numel() // C
+        y = out.t if out is not None else _empty(x.shape, x)
+        y2, ldy = _rows(y, C)
+        assert y2.data_ptr() == y.data_ptr()
+        add2, ldadd = (None, 0) if add is None else _rows(add, C)
+        ctx.s = _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2, ldadd, cmap, pmap)
+        ctx.bn = bn
+        ctx.has_add = add is not None
+        ctx.xshape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s = ctx.s
+        dy2, lddy = _rows(dy, s.C)
+        dadd = _empty(ctx.xshape, dy) if (ctx.has_add and ctx.needs_input_grad[1]) else None
+        dx = _bn_backward(s, ctx.bn, dy2, lddy, ctx.needs_input_grad[0], dadd, s.C)
+        if dx is not None:
+            dx = dx.view(ctx.xshape)
+        return dx, dadd, None, None, None, None, None, None, None, None, None
+
+
+def bn_act(x, bn, act=ACT_NONE, slope=0.0, add=None, cmap=None, pmap=None, out=None):
+    return BnActFn.apply(x, add, bn.weight, bn.bias, bn, bn.training, act, slope, cmap, pmap,
+                         None if out is None else Out(out))
+
+
+# ------------------------------------------------------------------------------------------ Conv (+BN +act)
+def _conv_out(L, k, s, p, d):
+    return (L + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class ConvBnActFn(torch.autograd.Function):
+    """channels-last Conv1d/Conv2d -> [BatchNorm] -> activation.
+    x: [N,H,W,Cin] (Conv1d: [N,L,Cin], handled as W=1); weight in the reference layout
+    [Cout,Cin,KH,KW] / [Cout,Cin,K].  Reference: WavEncoder/MFCCEncoder/AffEncoder/STGraphConv."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, conv, bn, training, act, slope, cmap, pmap, out):
+        _check(x, w, b)
+        is1d = x.dim() == 3
+        N, H = x.shape[0], x.shape[1]
+        W = 1 if is1d else x.shape[2]
+        Cin = x.shape[-1]
+        Cout = w.shape[0]
+        KH, KW = (w.shape[2], 1) if is1d else (w.shape[2], w.shape[3])
+        sh, sw, ph, pw, dh, dw = conv
+        Ho, Wo = _conv_out(H, KH, sh, ph, dh), _conv_out(W, KW, sw, pw, dw)
+        x2, ldx = _rows(x, Cin)
+        oshape = (N, Ho, Cout) if is1d else (N, Ho, Wo, Cout)
+        st = _stream(x)
+        M = N * Ho * Wo
+        if bn is None:
+            y = out.t if out is not None else _empty(oshape, x)
+            y2, ldy = _rows(y, Cout)
+            _C.call("s2ag_conv_fwd", _p(x2), ldx, N, H, W, Cin, _p(w), _p(b), _p(y2), ldy, Cout, KH, KW, sh, sw, ph,
+                    pw, dh, dw, act, float(slope), st)
+            ctx.s = None
+            ctx.c = None
+        else:
+            c = _empty((M, Cout), x)
+            _C.call("s2ag_conv_fwd", _p(x2), ldx, N, H, W, Cin, _p(w), _p(b), _p(c), Cout, Cout, KH, KW, sh, sw, ph, pw,
+                    dh, dw, ACT_NONE, 0.0, st)
+            y = out.t if out is not None else _empty(oshape, x)
+            y2, ldy = _rows(y, Cout)
+            ctx.s = _bn_forward(c, Cout, M, Cout, bn, training, act, slope, y2, ldy, None, 0, cmap, pmap)
+        assert y2.data_ptr() == y.data_ptr()
+        ctx.bn = bn
+        ctx.geom = (N, H, W, Cin, Cout, KH, KW, sh, sw, ph, pw, dh, dw, M, act, float(slope), ldx, ldy)
+        ctx.x2, ctx.w, ctx.b, ctx.y2 = x2, w, b, y2
+        ctx.xshape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, Cin, Cout, KH, KW, sh, sw, ph, pw, dh, dw, M, act, slope, ldx, ldy = ctx.geom
+        st = _stream(dy)
+        dy2, lddy = _rows(dy, Cout)
+        if ctx.s is not None:
+            dc = _bn_backward(ctx.s, ctx.bn, dy2, lddy, True)
+            lddc = Cout
+        elif act != ACT_NONE:
+            dc = _empty((M, Cout), dy)
+            _C.call("s2ag_act_bwd", _p(dy2), lddy, _p(ctx.y2), ldy, _p(dc), Cout, M, Cout, act, slope, st)
+            lddc = Cout
+        else:
+            dc, lddc = dy2, lddy
+        w, b = ctx.w, ctx.b
+        if w.requires_grad:
+            db = _grad_of(b) if (b is not None and b.requires_grad) else None
+            _C.call("s2ag_conv_bwd_weight", _p(dc), lddc, _p(ctx.x2), ldx, N, H, W, Cin, _p(_grad_of(w)), _p(db), Cout,
+                    KH, KW, sh, sw, ph, pw, dh, dw, st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if sh != 1 or sw != 1:
+                raise _C.S2agError("conv data-gradient implemented for stride 1 only (strided convs are frozen)")
+            dx = _empty(ctx.xshape, dy)
+            _C.call("s2ag_conv_bwd_data", _p(dc), lddc, N, H, W, Cin, _p(w), _p(dx), Cin, Cout, KH, KW, ph, pw, dh, dw,
+                    0, st)
+        return (dx,) + (None,) * 12
+
+
+def conv_bn_act(x, conv_w, conv_b, geom, bn=None, act=ACT_NONE, slope=0.0, cmap=None, pmap=None, out=None):
+    """geom = (sh, sw, ph, pw, dh, dw)"""
+    g, be, tr = (None, None, False) if bn is None else (bn.weight, bn.bias, bn.training)
+    return ConvBnActFn.apply(x, conv_w, conv_b, g, be, tuple(geom), bn, tr, act, slope, cmap, pmap,
+                             None if out is None else Out(out))
+
+
+# ------------------------------------------------------------------------------------------ ST-GCN graph contraction
+class GraphFn(torch.autograd.Function):
+    """y[n,t,w,c] = sum_{k,v} x[n,t,v,k*C+c] A[k,v,w]   (net/utils/tgcn.py:66-69)"""
+
+    @staticmethod
+    def forward(ctx, x, A):
+        _check(x, A)
+        K, V, _ = A.shape
+        KC = x.shape[-1]
+        C = KC // K
+        x = x.contiguous()
+        M = x.numel() // (V * KC)
+        y = _empty(x.shape[:-1] + (C,), x)
+        _C.call("s2ag_graph_fwd", _p(x), _p(A), _p(y), M, V, K, C, _stream(x))
+        ctx.A = A
+        ctx.dims = (M, V, K, C, x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        M, V, K, C, xshape = ctx.dims
+        dy = dy.contiguous()
+        dx = _empty(xshape, dy)
+        _C.call("s2ag_graph_bwd", _p(dy), _p(ctx.A), _p(dx), M, V, K, C, _stream(dy))
+        return dx, None
+
+
+def graph_contract(x, A):
+    return GraphFn.apply(x, A)
+
+
+# ------------------------------------------------------------------------------------------ Embedding
+class EmbeddingFn(torch.autograd.Function):
+    """out = dropout(table[idx])   (net/multimodal_context_net_v2.py:88, :513)"""
+
+    @staticmethod
+    def forward(ctx, idx, table, p, seed):
+        _check(idx, table)
+        idx = idx.contiguous()
+        V, D = table.shape
+        out = _empty(tuple(idx.shape) + (D,), table)
+        nonce = seed_nonce(table.device) if p > 0 else None
+        _C.call("s2ag_embedding_fwd", _p(idx), _p(table), _p(out), D, idx.numel(), D, V, float(p),
+                ctypes.c_uint64(seed), _p(nonce), _stream(table))
+        ctx.idx, ctx.table = idx, table
+        ctx.cfg = (float(p), seed, V, D, nonce)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, seed, V, D, nonce = ctx.cfg
+        if ctx.table.requires_grad:
+            d2, ld = _rows(dout, D)
+            _C.call("s2ag_embedding_bwd", _p(ctx.idx), _p(d2), ld, _p(_grad_of(ctx.table)), ctx.idx.numel(), D, V, p,
+                    ctypes.c_uint64(seed), _p(nonce), _stream(dout))
+        return None, None, None, None
+
+
+def embedding(idx, table, p=0.0):
+    return EmbeddingFn.apply(idx, table, p, next_seed() if p > 0 else 0)
+
+
+# ------------------------------------------------------------------------------------------ Dropout
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        _check(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        nonce = seed_nonce(x.device)
+        _C.call("s2ag_dropout", _p(x), _p(y), x.numel(), float(p), ctypes.c_uint64(seed), _p(nonce), _stream(x))
+        ctx.cfg = (float(p), seed, nonce)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, nonce = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        _C.call("s2ag_dropout", _p(dy), _p(dx), dy.numel(), p, ctypes.c_uint64(seed), _p(nonce), _stream(dy))
+        return dx, None, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0:
+        return x
+    return DropoutFn.apply(x, p, next_seed())
+
+
+# ------------------------------------------------------------------------------------------ TCN residual block
+class TcnBlockFn(torch.autograd.Function):
+    """weight_norm + TemporalBlock (net/tcn.py:16-46) over channels-last x[B,T,C]."""
+
+    @staticmethod
+    def forward(ctx, x, v1, g1, b1, v2, g2, b2, dilation, p, seed):
+        _check(x, v1, g1, b1, v2, g2, b2)
+        x = x.contiguous()
+        B, T, C = x.shape
+        k = v1.shape[2]
+        if k != 2 or v1.shape[0] != C or v1.shape[1] != C:
+            raise _C.S2agError("TCN block kernel supports kernel_size=2 and n_inputs == n_outputs")
+        st = _stream(x)
+        w1, w2 = _empty((C, k, C), x), _empty((C, k, C), x)
+        n1, n2 = _empty((C,), x), _empty((C,), x)
+        _C.call("s2ag_weight_norm_fwd", _p(v1), _p(g1), _p(w1), _p(n1), C, C, k, st)
+        _C.call("s2ag_weight_norm_fwd", _p(v2), _p(g2), _p(w2), _p(n2), C, C, k, st)
+        y1, y2, out = _empty(x.shape, x), _empty(x.shape, x), _empty(x.shape, x)
+        nonce = seed_nonce(x.device) if p > 0 else None
+        _C.call("s2ag_tcn_block_fwd", _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y1), _p(y2), _p(out), B, T, C, dilation,
+                float(p), ctypes.c_uint64(seed), _p(nonce), st)
+        ctx.t = (x, y1, y2, out, w1, w2, n1, n2, v1, g1, b1, v2, g2, b2)
+        ctx.cfg = (B, T, C, k, dilation, float(p))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, y2, out, w1, w2, n1, n2, v1, g1, b1, v2, g2, b2 = ctx.t
+        B, T, C, k, dilation, p = ctx.cfg
+        st = _stream(dout)
+        dout = dout.contiguous()
+        dx = _empty(x.shape, x)
+        dw = torch.zeros((2, C, k, C), dtype=torch.float32, device=x.device)
+        ws = _empty((2, B * T * C), x)
+        train_w = v1.requires_grad
+        db1 = _grad_of(b1) if train_w else torch.zeros_like(b1)
+        db2 = _grad_of(b2) if train_w else torch.zeros_like(b2)
+        _C.call("s2ag_tcn_block_bwd", _p(dout), _p(x), _p(y1), _p(y2), _p(out), _p(w1), _p(w2), _p(dx), _p(dw[0]),
+                _p(db1), _p(dw[1]), _p(db2), _p(ws), B, T, C, dilation, p, st)
+        if train_w:
+            _C.call("s2ag_weight_norm_bwd", _p(dw[0]), _p(v1), _p(g1), _p(n1), _p(_grad_of(v1)), _p(_grad_of(g1)), C, C,
+                    k, st)
+            _C.call("s2ag_weight_norm_bwd", _p(dw[1]), _p(v2), _p(g2), _p(n2), _p(_grad_of(v2)), _p(_grad_of(g2)), C, C,
+                    k, st)
+        return (dx,) + (None,) * 9
+
+
+def tcn_block(x, v1, g1, b1, v2, g2, b2, dilation, p, training):
+    p = p if training else 0.0
+    return TcnBlockFn.apply(x, v1, g1, b1, v2, g2, b2, dilation, p, next_seed() if p > 0 else 0)
+
+
+# ------------------------------------------------------------------------------------------ bidirectional multi-layer GRU
+class BiGruFn(torch.autograd.Function):
+    """nn.GRU(num_layers=L, bidirectional=True, batch_first=True, dropout=p), h0 = 0.
+    `x` is the full [B,T,In] input buffer; `pieces` are the differentiable tensors that were
+    written into column slices of it (so the concat is never materialised and the backward hands
+    each producer a view of dx).  Output [B,T,2H], or [B,T,H] = fwd+rev when sum_halves.
+    params: flat list per layer of (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)."""
+
+    @staticmethod
+    def forward(ctx, x, slices, nlayers, H, p, training, sum_halves, *rest):
+        params = rest[:8 * nlayers]
+        pieces = rest[8 * nlayers:]
+        _check(x, *params)
+        B, T, In0 = x.shape
+        x2, ldx = _rows(x, In0)
+        st = _stream(x)
+        need_bwd = any(ctx.needs_input_grad)
+        gi_ws = _empty((B * T * 6 * H,), x)
+        layers = []
+        cur, ldcur, In = x2, ldx, In0
+        for l in range(nlayers):
+            wif, whf, bif, bhf, wir, whr, bir, bhr = params[8 * l:8 * l + 8]
+            out = _empty((B, T, 2 * H), x)
+            gates = _empty((B * T * 2 * 4 * H,), x) if need_bwd else None
+            _C.call("s2ag_gru_layer_fwd", _p(cur), ldcur, _p(wif), _p(wir), _p(bif), _p(bir), _p(whf), _p(whr), _p(bhf),
+                    _p(bhr), _p(gi_ws), _p(out), _p(gates), B, T, In, H, st)
+            rec = {"x": cur, "ldx": ldcur, "In": In, "out": out, "gates": gates, "drop": None}
+            nxt = out
+            if training and p > 0 and l < nlayers - 1:
+                seed = next_seed()
+                nonce = seed_nonce(x.device)
+                nxt = torch.empty_like(out)
+                _C.call("s2ag_dropout", _p(out), _p(nxt), out.numel(), float(p), ctypes.c_uint64(seed), _p(nonce), st)
+                rec["drop"] = (float(p), seed, nonce)
+            layers.append(rec)
+            cur, ldcur, In = nxt, 2 * H, 2 * H
+        last = layers[-1]["out"]
+        if sum_halves:
+            y = _empty((B, T, H), x)
+            _C.call("s2ag_add_halves", _p(last), _p(y), B * T, H, st)
+        else:
+            y = last
+        if need_bwd:
+            ctx.layers, ctx.params = layers, params
+            ctx.cfg = (B, T, In0, H, nlayers, sum_halves, slices, len(pieces))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, In0, H, nlayers, sum_halves, slices, npieces = ctx.cfg
+        st = _stream(dy)
+        M = B * T
+        ws = _empty((M * 12 * H + 4 * B * H,), dy)
+        if sum_halves:
+            d, ldd = _rows(dy, H)
+            dstride = 0
+        else:
+            d, ldd = _rows(dy, 2 * H)
+            dstride = H
+        dx = None
+        for l in range(nlayers - 1, -1, -1):
+            rec = ctx.layers[l]
+            wif, whf, bif, bhf, wir, whr, bir, bhr = ctx.params[8 * l:8 * l + 8]
+            need_dx = l > 0 or npieces > 0 or ctx.needs_input_grad[0]
+            dxl = _empty((B, T, rec["In"]), dy) if need_dx else None
+            if not wif.requires_grad:
+                raise _C.S2agError("GRU backward through frozen weights is not on the reference path")
+            _C.call("s2ag_gru_layer_bwd", _p(d), ldd, dstride, _p(rec["x"]), rec["ldx"], _p(rec["out"]), _p(rec["gates"]),
+                    _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"],
+                    _p(_grad_of(wif)), _p(_grad_of(wir)), _p(_grad_of(bif)), _p(_grad_of(bir)),
+                    _p(_grad_of(whf)), _p(_grad_of(whr)), _p(_grad_of(bhf)), _p(_grad_of(bhr)), _p(ws),
+                    B, T, rec["In"], H, st)
+            if l > 0:
+                drop = ctx.layers[l - 1]["drop"]
+                if drop is not None:
+                    pp, seed, nonce = drop
+                    _C.call("s2ag_dropout", _p(dxl), _p(dxl), dxl.numel(), pp, ctypes.c_uint64(seed), _p(nonce), st)
+                d, ldd, dstride = dxl, 2 * H, H
+            else:
+                dx = dxl
+        grads = [dx if ctx.needs_input_grad[0] else None, None, None, None, None, None, None]
+        grads += [None] * (8 * nlayers)
+        for (a, b_) in slices:
+            grads.append(dx[:, :, a:b_])
+        return tuple(grads)
+
+
+def bigru(x, gru_params, nlayers, H, p, training, sum_halves=False, pieces=(), slices=()):
+    return BiGruFn.apply(x, tuple(slices), nlayers, H, p, training, sum_halves, *gru_params, *pieces)
+
+
+# ------------------------------------------------------------------------------------------ speaker z
+class ReparamTileFn(torch.autograd.Function):
+    """z = mu + eps*exp(0.5*logvar) and its tiling over T into columns [off, off+Z) of `dst`
+    (net/embedding_net.py:10-13; net/multimodal_context_net_v2.py:536-539).  Returns (z, dst_slice)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, dst, off):
+        dst = dst.t
+        _check(mu, logvar, eps, dst)
+        B, Z = mu.shape
+        mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
+        z = _empty((B, Z), mu)
+        T = dst.shape[1]
+        d2, ld = _rows(dst, dst.shape[-1])
+        _C.call("s2ag_reparam_tile_fwd", _p(mu), _p(logvar), _p(eps), _p(z), _p(d2), ld, off, B, T, Z, _stream(mu))
+        ctx.t = (logvar, eps)
+        ctx.cfg = (B, T, Z, off)
+        return z, col_slice(dst, off, off + Z)
+
+    @staticmethod
+    def backward(ctx, dz, dsl):
+        logvar, eps = ctx.t
+        B, T, Z, off = ctx.cfg
+        dmu, dlv = _empty((B, Z), logvar), _empty((B, Z), logvar)
+        if dsl is not None:
+            d2, ld = _rows(dsl, Z)
+        else:
+            d2, ld = None, 0
+        dz = dz.contiguous() if dz is not None else None
+        _C.call("s2ag_reparam_tile_bwd", _p(d2), ld, 0, _p(dz), _p(logvar), _p(eps), _p(dmu), _p(dlv), B, T, Z,
+                _stream(logvar))
+        return dmu, dlv, None, None, None
+
+
+def reparam_tile(mu, logvar, eps, dst, off):
+    return ReparamTileFn.apply(mu, logvar, eps, Out(dst), off)
+
+
+# ------------------------------------------------------------------------------------------ discriminator head
+class DHeadFn(torch.autograd.Function):
+    """sigmoid(out2(out(fwd+rev)))  (net/multimodal_context_net_v2.py:579-585)"""
+
+    @staticmethod
+    def forward(ctx, g, w1, b1, w2, b2):
+        _check(g, w1, b1, w2, b2)
+        g = g.contiguous()
+        B, T, H2 = g.shape
+        H = H2 // 2
+        lin1 = _empty((B, T), g)
+        out = _empty((B, 1), g)
+        _C.call("s2ag_dhead_fwd", _p(g), _p(w1), _p(b1), _p(w2), _p(b2), _p(lin1), _p(out), B, T, H, _stream(g))
+        ctx.t = (g, lin1, out, w1, b1, w2, b2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, lin1, out, w1, b1, w2, b2 = ctx.t
+        B, T, H2 = g.shape
+        dout = dout.contiguous()
+        dg = _empty(g.shape, g) if ctx.needs_input_grad[0] else None
+        if w1.requires_grad:
+            gw1, gb1, gw2, gb2 = _grad_of(w1), _grad_of(b1), _grad_of(w2), _grad_of(b2)
+        else:
+            gw1, gb1, gw2, gb2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2)
+        _C.call("s2ag_dhead_bwd", _p(dout), _p(out), _p(g), _p(lin1), _p(w1), _p(w2), _p(dg), _p(gw1), _p(gb1), _p(gw2),
+                _p(gb2), B, T, H2 // 2, _stream(g))
+        return dg, None, None, None, None
+
+
+def dhead(g, w1, b1, w2, b2):
+    return DHeadFn.apply(g, w1, b1, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------ losses / optimiser / metric
+def dis_loss(d_real, d_fake, loss_out, want_grads=True):
+    """processor_v2.py:811.  loss_out: float[1] device slot.  -> (g_real, g_fake)"""
+    B = d_real.shape[0]
+    gr = torch.empty_like(d_real) if want_grads else None
+    gf = torch.empty_like(d_fake) if want_grads else None
+    _C.call("s2ag_dis_loss", _p(d_real.contiguous()), _p(d_fake.contiguous()), _p(loss_out), _p(gr), _p(gf), B,
+            _stream(d_real))
+    return gr, gf
+
+
+def gen_loss(out, tgt, out_rand, z, z_rand, mu, logvar, dis_out, weights, losses_out, want_grads=True):
+    """processor_v2.py:893-937.  weights = (w_huber, w_kld, w_div, w_gan); losses_out: float[5]
+    (huber, gen, kld, div_reg, total).  -> (g_out, g_dis, g_mu, g_logvar)"""
+    B = out.shape[0]
+    TP = out.numel() // B
+    Z = 0 if z is None else z.shape[1]
+    out, tgt = out.contiguous(), tgt.contiguous()
+    g_out = torch.empty_like(out) if want_grads else None
+    g_dis = torch.empty_like(dis_out) if (want_grads and dis_out is not None) else None
+    g_mu = torch.empty_like(mu) if (want_grads and mu is not None) else None
+    g_lv = torch.empty_like(logvar) if (want_grads and logvar is not None) else None
+    c = lambda t: None if t is None else t.contiguous()
+    _C.call("s2ag_gen_loss", _p(out), _p(tgt), _p(c(out_rand)), _p(c(z)), _p(c(z_rand)), _p(c(mu)), _p(c(logvar)),
+            _p(c(dis_out)), float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
+            _p(losses_out), _p(g_out), _p(g_dis), _p(g_mu), _p(g_lv), B, TP, Z, _stream(out))
+    return g_out, g_dis, g_mu, g_lv
+
+
+def l1_mean(a, b, dst):
+    a, b = a.contiguous(), b.contiguous()
+    _C.call("s2ag_l1_mean", _p(a), _p(b), _p(dst), a.numel(), _stream(a))
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count, grad_scale=1.0):
+    """Flat-buffer Adam (processor_v2.py:215-220).  step_count: int32[1] device tensor."""
+    _C.call("s2ag_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+            float(grad_scale), _p(step_count), _stream(p))
+
+
+def attention(x, w1, b1, w2, b2):
+    """sigmoid-MLP score + softmax over time + weighted sum (net/ser_att_conv_rnn_v2.py:30-34).
+    -> (out[N,Hd], alphas[N,T,1])"""
+    _check(x, w1, b1, w2, b2)
+    x = x.contiguous()
+    N, T, Hd = x.shape
+    A = w1.shape[0]
+    out = _empty((N, Hd), x)
+    alpha = _empty((N, T, 1), x)
+    _C.call("s2ag_attention_fwd", _p(x), _p(w1.contiguous()), _p(b1), _p(w2.contiguous()), _p(b2), _p(out), _p(alpha),
+            N, T, Hd, A, _stream(x))
+    return out, alpha
