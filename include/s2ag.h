@@ -45,6 +45,17 @@ int s2ag_linear_bwd_data(const float* dy, long lddy, const float* w, float* dx, 
 /* dw[N,K] += dy^T x ; db[N] += colsum(dy) (db may be NULL) */
 int s2ag_linear_bwd_weight(const float* dy, long lddy, const float* x, long ldx, float* dw, float* db,
                            int M, int N, int K, void* stream);
+/* Linear over the ROW axis of each batch item (MFCCEncoder.linear1, :49,57: the reference applies
+ * Linear(num_mfcc -> 32) to the last axis of [B, C, L]; channels-last holds that tensor as x[B, L, C]):
+ *   y[b, c, n] = act( sum_l x[b, l, c] * w[n, l] + bias[n] ),   y row (b,c) at y + (b*C + c)*ldy */
+int s2ag_linear_t_fwd(const float* x, const float* w, const float* bias, float* y, long ldy,
+                      int B, int L, int C, int N, int act, float slope, void* stream);
+/* dx[b, l, c] = sum_n dy[b, c, n] w[n, l] */
+int s2ag_linear_t_bwd_data(const float* dy, long lddy, const float* w, float* dx,
+                           int B, int L, int C, int N, void* stream);
+/* dw[n, l] += sum_{b,c} dy[b, c, n] x[b, l, c] ; db[n] += sum_{b,c} dy[b, c, n] */
+int s2ag_linear_t_bwd_weight(const float* dy, long lddy, const float* x, float* dw, float* db,
+                             int B, int L, int C, int N, void* stream);
 /* dpre = dy * act'(y) evaluated from the activation OUTPUT y; [M,N] with row strides */
 int s2ag_act_bwd(const float* dy, long lddy, const float* y, long ldy, float* dpre, long ldd,
                  int M, int N, int act, float slope, void* stream);
@@ -139,7 +150,8 @@ int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const floa
                        int B, int T, int In, int H, void* stream);
 /* dout[B,T,*]: gradient of the layer output; direction `d` reads columns d*dir_stride .. +H of a
  * row of stride lddout (dir_stride = H normally; 0 when both halves share the gradient of their
- * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += .
+ * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += ; pass all eight as NULL to
+ * skip the parameter gradients (discriminator inside the generator step).
  * ws: float[B*T*6H (dgi) + B*T*6H (dgh) + 4*B*H (dh ping-pong)] */
 int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride, const float* x, long ldx,
                        const float* out, const float* gates,

@@ -71,6 +71,43 @@ extern "C" int s2ag_linear_bwd_weight(const float* dy, long lddy, const float* x
   return S2AG_OK;
 }
 
+// ------------------------------------------------------------------ Linear over the row axis (batched, A transposed)
+extern "C" int s2ag_linear_t_fwd(const float* x, const float* w, const float* bias, float* y, long ldy,
+                                 int B, int L, int C, int N, int act, float slope, void* stream) {
+  S2AG_CHECK_ARG(x && w && y && B >= 0 && L > 0 && C > 0 && N > 0 && ldy >= N);
+  if (B == 0) return S2AG_OK;
+  LdPlain<false> a{x, 1, (long)C, (long)L * C};  // element(row=c, k=l) = x[b][l][c]
+  LdPlain<true> b{w, (long)L, 1, 0};
+  EpiGeneric e = make_epi(y, ldy, bias, act, slope, 0);
+  e.bstride = (long)C * ldy;
+  launch_gemm(a, b, e, C, N, L, B, 1, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+extern "C" int s2ag_linear_t_bwd_data(const float* dy, long lddy, const float* w, float* dx,
+                                      int B, int L, int C, int N, void* stream) {
+  S2AG_CHECK_ARG(dy && w && dx && B >= 0 && L > 0 && C > 0 && N > 0 && lddy >= N);
+  if (B == 0) return S2AG_OK;
+  LdPlain<false> a{w, 1, (long)L, 0};                 // element(row=l, k=n) = w[n][l]
+  LdPlain<true> b{dy, lddy, 1, (long)C * lddy};       // element(row=c, k=n) = dy[b][c][n]
+  EpiGeneric e = make_epi(dx, (long)C);
+  e.bstride = (long)L * C;
+  launch_gemm(a, b, e, L, C, N, B, 1, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+extern "C" int s2ag_linear_t_bwd_weight(const float* dy, long lddy, const float* x, float* dw, float* db,
+                                        int B, int L, int C, int N, void* stream) {
+  S2AG_CHECK_ARG(dy && x && dw && B >= 0 && L > 0 && C > 0 && N > 0 && lddy >= N);
+  if (B == 0) return S2AG_OK;
+  LdPlain<false> a{dy, 1, lddy, (long)C * lddy};      // element(row=n, k=c) = dy[b][c][n]
+  LdPlain<true> b{x, (long)C, 1, (long)L * C};        // element(row=l, k=c) = x[b][l][c]
+  launch_gemm(a, b, make_epi(dw, (long)L, nullptr, 0, 0.f, 2), N, L, C, B, 1, stream);
+  if (db) launch_colsum(dy, lddy, db, B * C, N, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
 // ------------------------------------------------------------------ elementwise helpers
 __global__ void act_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ y, long ldy,
                                float* __restrict__ dpre, long ldd, int M, int N, int act, float slope) {

@@ -148,7 +148,8 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
                                   float* dw_hh_f, float* dw_hh_r, float* db_hh_f, float* db_hh_r, float* ws,
                                   int B, int T, int In, int H, void* stream) {
   S2AG_CHECK_ARG(dout && x && out && gates && w_ih_f && w_ih_r && w_hh_f && w_hh_r && ws);
-  S2AG_CHECK_ARG(dw_ih_f && dw_ih_r && db_ih_f && db_ih_r && dw_hh_f && dw_hh_r && db_hh_f && db_hh_r);
+  const bool want_w = dw_ih_f != nullptr;  // all eight weight-gradient pointers or none
+  S2AG_CHECK_ARG(!want_w || (dw_ih_r && db_ih_f && db_ih_r && dw_hh_f && dw_hh_r && db_hh_f && db_hh_r));
   S2AG_CHECK_ARG(B >= 0 && T > 0 && In > 0 && H > 0 && ldx >= In);
   if (B == 0) return S2AG_OK;
   const int M = B * T;
@@ -180,7 +181,7 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
   float* db_ih[2] = {db_ih_f, db_ih_r};
   float* dw_hh[2] = {dw_hh_f, dw_hh_r};
   float* db_hh[2] = {db_hh_f, db_hh_r};
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < 2 && want_w; ++d) {
     {  // dW_ih[d][3H, In] += dgi_d^T @ x
       LdPlain<false> a{dgi + (long)d * 3 * H, 1, 6L * H, 0};
       LdPlain<false> b{x, 1, ldx, 0};

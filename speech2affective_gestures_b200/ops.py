@@ -162,6 +162,49 @@ def linear(x, w, b=None, act=ACT_NONE, slope=0.0, out=None):
     return LinearFn.apply(x, w, b, act, slope, None if out is None else Out(out))
 
 
+class LinearTFn(torch.autograd.Function):
+    """MFCCEncoder.linear1 (net/multimodal_context_net_v2.py:49,57) on channels-last data:
+    y[b,c,:] = act(w @ x[b,:,c] + bias);  x[B,L,C] -> y[B,C,N] (optionally into a column slice)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, slope, out):
+        _check(x, w, b)
+        x = x.contiguous()
+        B, L, C = x.shape
+        N = w.shape[0]
+        y = out.t if out is not None else _empty((B, C, N), x)
+        yr, ldy = _rows(y, N)
+        assert yr.data_ptr() == y.data_ptr()
+        _C.call("s2ag_linear_t_fwd", _p(x), _p(w), _p(b), _p(yr), ldy, B, L, C, N, act, float(slope), _stream(x))
+        ctx.t = (x, w, b, y)
+        ctx.cfg = (B, L, C, N, act, float(slope))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, y = ctx.t
+        B, L, C, N, act, slope = ctx.cfg
+        st = _stream(dy)
+        dyr, lddy = _rows(dy, N)
+        if act != ACT_NONE:
+            yr, ldy = _rows(y, N)
+            dpre = _empty((B * C, N), dy)
+            _C.call("s2ag_act_bwd", _p(dyr), lddy, _p(yr), ldy, _p(dpre), N, B * C, N, act, slope, st)
+            dyr, lddy = dpre, N
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty((B, L, C), dy)
+            _C.call("s2ag_linear_t_bwd_data", _p(dyr), lddy, _p(w), _p(dx), B, L, C, N, st)
+        if w.requires_grad:
+            db = _grad_of(b) if (b is not None and b.requires_grad) else None
+            _C.call("s2ag_linear_t_bwd_weight", _p(dyr), lddy, _p(x), _p(_grad_of(w)), _p(db), B, L, C, N, st)
+        return dx, None, None, None, None, None
+
+
+def linear_t(x, w, b=None, act=ACT_NONE, slope=0.0, out=None):
+    return LinearTFn.apply(x, w, b, act, slope, None if out is None else Out(out))
+
+
 # ------------------------------------------------------------------------------------------ BatchNorm helper
 class _BnState:
     """The per-call record a BN forward leaves for its backward."""
@@ -519,13 +562,10 @@ class BiGruFn(torch.autograd.Function):
             wif, whf, bif, bhf, wir, whr, bir, bhr = ctx.params[8 * l:8 * l + 8]
             need_dx = l > 0 or npieces > 0 or ctx.needs_input_grad[0]
             dxl = _empty((B, T, rec["In"]), dy) if need_dx else None
-            if not wif.requires_grad:
-                raise _C.S2agError("GRU backward through frozen weights is not on the reference path")
+            gw = [_p(_grad_of(q)) for q in (wif, wir, bif, bir, whf, whr, bhf, bhr)] if wif.requires_grad \
+                else [None] * 8
             _C.call("s2ag_gru_layer_bwd", _p(d), ldd, dstride, _p(rec["x"]), rec["ldx"], _p(rec["out"]), _p(rec["gates"]),
-                    _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"],
-                    _p(_grad_of(wif)), _p(_grad_of(wir)), _p(_grad_of(bif)), _p(_grad_of(bir)),
-                    _p(_grad_of(whf)), _p(_grad_of(whr)), _p(_grad_of(bhf)), _p(_grad_of(bhr)), _p(ws),
-                    B, T, rec["In"], H, st)
+                    _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"], *gw, _p(ws), B, T, rec["In"], H, st)
             if l > 0:
                 drop = ctx.layers[l - 1]["drop"]
                 if drop is not None:
@@ -541,8 +581,12 @@ class BiGruFn(torch.autograd.Function):
         return tuple(grads)
 
 
-def bigru(x, gru_params, nlayers, H, p, training, sum_halves=False, pieces=(), slices=()):
-    return BiGruFn.apply(x, tuple(slices), nlayers, H, p, training, sum_halves, *gru_params, *pieces)
+def bigru(x, gru_params, nlayers, H, p, training, sum_halves=False, pieces=None, slices=None):
+    """x: [B,T,In] input buffer.  pieces/slices: the differentiable producers of its column ranges
+    (default: x itself as one piece)."""
+    if pieces is None:
+        pieces, slices = (x,), ((0, x.shape[-1]),)
+    return BiGruFn.apply(x.detach(), tuple(slices), nlayers, H, p, training, sum_halves, *gru_params, *pieces)
 
 
 # ------------------------------------------------------------------------------------------ speaker z

@@ -1,0 +1,457 @@
+"""Drop-in for the hot-path entry points of the reference's processor_v2.py `Processor`:
+constructor, `forward_pass_s2ag` (one GAN iteration, :776-957), `per_train_epoch` / `per_val_epoch` /
+`train` (:959-1069), `yield_batch` (:589-638), `generate_gestures` (:1071-1142) and a lock-step
+batched version of the long-form chunked synthesis of `render_clip` (:1144-1331).
+
+Out of scope: LMDB/npz cache writers, video rendering, FGD evaluator, BVH export.
+
+Execution model (B200-first): one process per GPU; every kernel of a step is enqueued on one
+stream with no host synchronisation (the reference's ~9 `.item()` syncs per step, :943-956, become
+one 8-float device buffer read on demand); the whole step can be captured once into a CUDA graph
+(`capture_step`) and replayed; gradients of a network are one flat buffer, all-reduced with a single
+NCCL call per optimiser when torch.distributed is initialised (replaces nn.DataParallel, :167-172);
+Adam runs as one kernel over the flat parameter buffer with device-side bias correction.
+"""
+import os
+import re
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .net import embedding_net as en
+from .net.multimodal_context_net_v2 import PoseGeneratorTriModal as PGT, ConvDiscriminatorTriModal as CDT, \
+    PoseGenerator, AffDiscriminator
+
+torch.manual_seed(1234)  # processor_v2.py:37
+ops.manual_seed(1234)
+
+# slots of Processor.metrics (device float32[8])
+M_DIS, M_HUBER, M_GEN, M_KLD, M_DIV, M_TOTAL, M_L1, M_L1_TRI = range(8)
+
+
+def get_epoch_and_loss(path_to_model_files, epoch='best'):
+    """Checkpoint discovery by filename, same scheme as processor_v2.py:53-83:
+    epoch_{:06d}_loss_{:.4f}_model.pth.tar; 'best' = lowest loss."""
+    if not os.path.isdir(path_to_model_files):
+        return None, None, np.inf
+    found = []
+    for f in os.listdir(path_to_model_files):
+        m = re.match(r"epoch_(\d+)_loss_([0-9.]+)_model\.pth\.tar$", f)
+        if m:
+            found.append((int(m.group(1)), float(m.group(2)), f))
+    if not found:
+        return None, None, np.inf
+    if epoch == 'best':
+        e, l, f = min(found, key=lambda r: r[1])
+    else:
+        cand = [r for r in found if r[0] == int(epoch)]
+        if not cand:
+            return None, None, np.inf
+        e, l, f = cand[0]
+    return f, e, l
+
+
+class _Log:
+    def __init__(self, work_dir, save_log=True, print_log=True):
+        self.work_dir, self.save_log, self.do_print = work_dir, save_log, print_log
+
+    def print_log(self, s):
+        if self.do_print:
+            print(s)
+        if self.save_log and self.work_dir:
+            os.makedirs(self.work_dir, exist_ok=True)
+            with open(os.path.join(self.work_dir, "log.txt"), "a") as f:
+                f.write(s + "\n")
+
+
+class Processor(object):
+    """Processor for emotive gesture generation (B200-native hot path)."""
+
+    def __init__(self, base_path, args, s2ag_config_args, data_loader, pose_dim, coords, audio_sr,
+                 min_train_epochs=20, zfill=6):
+        self.base_path = base_path
+        self.args = args
+        if getattr(args, "no_cuda", False) or not torch.cuda.is_available():
+            from . import _C
+            if not _C.is_emulated():
+                raise _C.S2agError("this Processor runs on a CUDA device only (no CPU fallback)")
+            self.device = torch.device("cpu")  # tests/emu: kernel-logic emulator injected explicitly
+        else:
+            self.device = torch.device('cuda:{}'.format(torch.cuda.current_device()))
+        self.s2ag_config_args = s2ag_config_args
+        self.data_loader = data_loader
+        self.result, self.iter_info, self.epoch_info = dict(), dict(), dict()
+        self.meta_info = dict(epoch=0, iter=0)
+        self.io = _Log(getattr(args, "work_dir_s2ag", None), getattr(args, "save_log", False),
+                       getattr(args, "print_log", True))
+        self.pose_dim, self.coords, self.audio_sr = pose_dim, coords, audio_sr
+
+        part = 'train_data_s2ag' if getattr(args, "train_s2ag", True) else 'test_data_s2ag'
+        d = self.data_loader[part]
+        self.time_steps = d.n_poses
+        self.audio_length = d.expected_audio_length
+        self.num_mfcc = d.num_mfcc_combined
+        self.lang_model = d.lang_model
+        self.mfcc_length = int(np.ceil(self.audio_length / 512))
+        self.best_s2ag_loss, self.best_s2ag_loss_epoch, self.s2ag_loss_updated = np.inf, None, False
+        self.min_train_epochs, self.zfill = min_train_epochs, zfill
+        self.train_speaker_model = self.data_loader['train_data_s2ag'].speaker_model
+        self.val_speaker_model = self.data_loader['val_data_s2ag'].speaker_model
+        self.test_speaker_model = self.data_loader['test_data_s2ag'].speaker_model
+
+        cfg = self.s2ag_config_args
+        self.trimodal_generator = PGT(cfg, pose_dim=pose_dim, n_words=self.lang_model.n_words,
+                                      word_embed_size=cfg.wordembed_dim,
+                                      word_embeddings=self.lang_model.word_embedding_weights,
+                                      z_obj=self.train_speaker_model)
+        self.trimodal_discriminator = CDT(pose_dim)  # constructed, never called (processor_v2.py:141)
+        self.use_mfcc = True
+        self.s2ag_generator = PoseGenerator(cfg, pose_dim=pose_dim, n_words=self.lang_model.n_words,
+                                            word_embed_size=cfg.wordembed_dim,
+                                            word_embeddings=self.lang_model.word_embedding_weights,
+                                            mfcc_length=self.mfcc_length, num_mfcc=self.num_mfcc,
+                                            time_steps=self.time_steps, z_obj=self.train_speaker_model)
+        self.s2ag_discriminator = AffDiscriminator(pose_dim)
+        for net in (self.trimodal_generator, self.trimodal_discriminator, self.s2ag_generator,
+                    self.s2ag_discriminator):
+            net.to(self.device)
+
+        self.train_samples = self.data_loader['train_data_s2ag'].samples
+        self.val_samples = self.data_loader['val_data_s2ag'].samples
+        self.num_train_samples = self.data_loader['train_data_s2ag'].n_samples
+        self.num_val_samples = self.data_loader['val_data_s2ag'].n_samples
+        self.num_test_samples = self.data_loader['test_data_s2ag'].n_samples
+
+        self.lr_s2ag_gen = cfg.learning_rate
+        self.lr_s2ag_dis = cfg.learning_rate * cfg.discriminator_lr_weight
+        self._init_optimizers()
+        self._init_distributed()
+        self.metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self.injected_rand_idx = None  # parity harness: fixed speaker permutation for processor_v2.py:903
+
+    # ------------------------------------------------------------------ optimiser / distributed state
+    def _init_optimizers(self):
+        """Adam(betas=(0.5, 0.999)) state for G and D over the flat buffers (processor_v2.py:215-220)."""
+        G, D = self.s2ag_generator, self.s2ag_discriminator
+        self.gen_m, self.gen_v = torch.zeros_like(G.flat_params), torch.zeros_like(G.flat_params)
+        self.dis_m, self.dis_v = torch.zeros_like(D.flat_params), torch.zeros_like(D.flat_params)
+        self.gen_step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.dis_step = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _init_distributed(self):
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if self.world > 1:  # one initial broadcast of weights and BN buffers
+            for net in (self.trimodal_generator, self.s2ag_generator, self.s2ag_discriminator):
+                dist.broadcast(net.flat_params, 0)
+                for b in net.buffers():
+                    if b.dtype == torch.float32:
+                        dist.broadcast(b, 0)
+
+    def _allreduce_grads(self, net):
+        """SUM over ranks; the 1/world average is folded into the Adam kernel's grad_scale."""
+        if self.world > 1:
+            dist.all_reduce(net.flat_grads)
+
+    # ------------------------------------------------------------------ one GAN iteration
+    def make_pre_seq(self, target_poses):
+        n_pre = self.s2ag_config_args.n_pre_poses
+        pre_seq = target_poses.new_zeros((target_poses.shape[0], target_poses.shape[1], target_poses.shape[2] + 1))
+        pre_seq[:, 0:n_pre, :-1] = target_poses[:, 0:n_pre]
+        pre_seq[:, 0:n_pre, -1] = 1  # indicating bit for constraints
+        return pre_seq
+
+    def gan_step_async(self, in_text, in_audio, in_mfcc, target_poses, vid_indices, train):
+        """processor_v2.py:776-957 without host synchronisation; results land in self.metrics and
+        self.last_out (generated poses of the main G pass) / self.last_out_trimodal."""
+        cfg = self.s2ag_config_args
+        G, D, Tri = self.s2ag_generator, self.s2ag_discriminator, self.trimodal_generator
+        m = self.metrics
+        gan_on = self.meta_info['epoch'] > cfg.loss_warmup and cfg.loss_gan_weight > 0.0
+        pre_seq = self.make_pre_seq(target_poses)
+        if train:
+            ops.advance_seed_nonce(self.device)
+
+        # ---- train D (processor_v2.py:791-814)
+        if gan_on:
+            if train:
+                D.zero_grad()
+            with torch.no_grad():  # the reference builds and discards this graph; only .detach() is used (:809)
+                out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices)
+            with torch.set_grad_enabled(train):
+                dis_real = D(target_poses, in_text)
+                dis_fake = D(out_for_d, in_text)
+            g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
+            if train:
+                torch.autograd.backward([dis_real, dis_fake], [g_real, g_fake])
+                self._allreduce_grads(D)
+                ops.adam_step(D.flat_params, D.flat_grads, self.dis_m, self.dis_v, self.lr_s2ag_dis, 0.5, 0.999,
+                              1e-8, self.dis_step, 1.0 / self.world)
+
+        # ---- train G (processor_v2.py:816-941)
+        if train:
+            G.zero_grad()
+        with torch.no_grad():
+            out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices)
+        with torch.set_grad_enabled(train):
+            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices)
+            # D's own parameter gradients from this pass are discarded by the reference (zero_grad at the
+            # next D step, :794), so they are not computed; gradients still flow through D into G.
+            d_params = [p for p in D.parameters() if p.requires_grad]
+            for p in d_params:
+                p.requires_grad_(False)
+            try:
+                dis_out = D(out, in_text)
+            finally:
+                for p in d_params:
+                    p.requires_grad_(True)
+        out_rand = z_rand = None
+        use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
+        if use_div:
+            if cfg.z_type == 'speaker':
+                rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
+                    torch.randperm(vid_indices.shape[0], device=vid_indices.device)
+                rand_vids = vid_indices[rand_idx]
+            else:
+                rand_vids = None
+            with torch.no_grad():  # only used detached (:913, :919)
+                out_rand, z_rand, _, _ = G(pre_seq, in_text, in_mfcc, rand_vids)
+        use_kld = use_div and cfg.z_type == 'speaker'
+        weights = (cfg.loss_regression_weight, cfg.loss_kld_weight if use_kld else 0.0,
+                   cfg.loss_reg_weight if use_div else 0.0, cfg.loss_gan_weight if gan_on else 0.0)
+        g_out, g_dis, g_mu, g_lv = ops.gen_loss(
+            out, target_poses, out_rand, z, z_rand, z_mu if use_kld else (z if use_div else None),
+            z_log_var if use_kld else (z if use_div else None), dis_out, weights,
+            m[M_HUBER:M_HUBER + 5], want_grads=train)
+        if train:
+            outs, grads = [out], [g_out]
+            if gan_on:
+                outs.append(dis_out); grads.append(g_dis)
+            if use_kld:
+                outs += [z_mu, z_log_var]; grads += [g_mu, g_lv]
+            torch.autograd.backward(outs, grads)
+            self._allreduce_grads(G)
+            ops.adam_step(G.flat_params, G.flat_grads, self.gen_m, self.gen_v, self.lr_s2ag_gen, 0.5, 0.999, 1e-8,
+                          self.gen_step, 1.0 / self.world)
+        ops.l1_mean(out.detach(), target_poses, m[M_L1:M_L1 + 1])
+        ops.l1_mean(out_tri, target_poses, m[M_L1_TRI:M_L1_TRI + 1])
+        self.last_out, self.last_out_trimodal = out.detach(), out_tri
+        return m
+
+    def forward_pass_s2ag(self, in_text, in_audio, in_mfcc, target_poses, vid_indices, train,
+                          target_seq=None, words=None, aux_info=None, save_path=None, make_video=False,
+                          calculate_metrics=False, losses_all_trimodal=None, joint_mae_trimodal=None,
+                          accel_trimodal=None, losses_all=None, joint_mae=None, accel=None):
+        """Same signature and return tuple as processor_v2.py:776-779, :956-957."""
+        if make_video:
+            raise NotImplementedError("video rendering is outside the hot path (SURVEY 8)")
+        m = self.gan_step_async(in_text, in_audio, in_mfcc, target_poses, vid_indices, train)
+        host = m.tolist()  # the single device->host read of the step
+        self.loss_dict = {'loss': self.s2ag_config_args.loss_regression_weight * host[M_HUBER],
+                          'KLD': self.s2ag_config_args.loss_kld_weight * host[M_KLD],
+                          'DIV_REG': self.s2ag_config_args.loss_reg_weight * host[M_DIV],
+                          'gen': self.s2ag_config_args.loss_gan_weight * host[M_GEN], 'dis': host[M_DIS]}
+        return host[M_L1] - host[M_L1_TRI], losses_all_trimodal, joint_mae_trimodal, accel_trimodal, losses_all, \
+            joint_mae, accel
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture_step(self, batch_size, train=True, warmup=3):
+        """Capture one whole GAN iteration (all forward/backward/Adam kernels, the NCCL all-reduces
+        when distributed, RNG draws) into a CUDA graph over static input buffers."""
+        assert self.device.type == "cuda"
+        T, P = self.time_steps, self.pose_dim
+        dev = self.device
+        self.static_in = (torch.zeros(batch_size, T, dtype=torch.int64, device=dev),
+                          torch.zeros(batch_size, self.audio_length, device=dev),
+                          torch.zeros(batch_size, self.num_mfcc, self.mfcc_length, device=dev),
+                          torch.zeros(batch_size, T, P, device=dev),
+                          torch.zeros(batch_size, dtype=torch.int64, device=dev))
+        self._graph_train = train
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.gan_step_async(*self.static_in, train)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.gan_step_async(*self.static_in, train)
+        return self._graph
+
+    def load_static_inputs(self, in_text, in_audio, in_mfcc, target_poses, vid_indices):
+        for dst, src in zip(self.static_in, (in_text, in_audio, in_mfcc, target_poses, vid_indices)):
+            dst.copy_(src, non_blocking=True)
+
+    def replay_step(self):
+        self._graph.replay()
+        return self.metrics
+
+    # ------------------------------------------------------------------ data / epochs
+    def _gather(self, samples, keys):
+        """npz-cache rows -> device tensors (processor_v2.py:601-611): int16 audio is rescaled on the
+        host exactly like the reference."""
+        dev = self.device
+        text = torch.from_numpy(samples['extended_word_seq'][keys]).to(dev)
+        vec = torch.from_numpy(samples['vec_seq'][keys]).float().to(dev)
+        audio = torch.from_numpy(samples['audio'][keys] * samples['audio_max'][keys, None] / 32767).float().to(dev)
+        mfcc = torch.from_numpy(samples['mfcc_features'][keys].astype(np.float32)).to(dev)
+        return text, vec, audio, mfcc, samples['vid_indices'][keys]
+
+    def yield_batch(self, train):
+        samples = self.train_samples if train else self.val_samples
+        num_data = self.num_train_samples if train else self.num_val_samples
+        spk = self.train_speaker_model if train else self.val_speaker_model
+        bs = self.args.batch_size
+        for _ in range((num_data + bs - 1) // bs):
+            keys = np.random.choice(num_data, size=bs, replace=True)
+            text, vec, audio, mfcc, cur_vids = self._gather(samples, keys)
+            vids = None
+            if spk is not None and spk.__class__.__name__ == 'Vocab':
+                pool = np.setdiff1d(list(spk.word2index.values()), cur_vids)  # speakers NOT in this batch (:625-630)
+                vids = torch.from_numpy(np.random.choice(pool, size=bs)).long().to(self.device)
+            yield text, vec, audio, mfcc, vids
+
+    def per_train_epoch(self):
+        self.s2ag_generator.train()
+        self.s2ag_discriminator.train()
+        total, n = 0., 0
+        self.meta_info['iter'] = 0
+        num_batches = self.num_train_samples // self.args.batch_size + 1
+        for text, vec, audio, mfcc, vids in self.yield_batch(train=True):
+            loss, *_ = self.forward_pass_s2ag(text, audio, mfcc, vec, vids, train=True)
+            total += loss
+            self.iter_info['s2ag_loss'] = loss
+            self.meta_info['iter'] += 1
+        self.epoch_info['mean_s2ag_loss'] = total / num_batches
+        self.io.print_log('\tmean_s2ag_loss: {}'.format(self.epoch_info['mean_s2ag_loss']))
+
+    def per_val_epoch(self):
+        self.s2ag_generator.eval()
+        self.s2ag_discriminator.eval()
+        total = 0.
+        num_batches = self.num_val_samples // self.args.batch_size + 1
+        for text, vec, audio, mfcc, vids in self.yield_batch(train=False):
+            with torch.no_grad():
+                loss, *_ = self.forward_pass_s2ag(text, audio, mfcc, vec, vids, train=False)
+            total += loss
+        self.epoch_info['mean_s2ag_loss'] = total / num_batches
+        if self.epoch_info['mean_s2ag_loss'] < self.best_s2ag_loss and self.meta_info['epoch'] > self.min_train_epochs:
+            self.best_s2ag_loss = self.epoch_info['mean_s2ag_loss']
+            self.best_s2ag_loss_epoch = self.meta_info['epoch']
+            self.s2ag_loss_updated = True
+        else:
+            self.s2ag_loss_updated = False
+
+    def load_model_at_epoch(self, epoch='best'):
+        name, e, l = get_epoch_and_loss(self.args.work_dir_s2ag, epoch=epoch)
+        if name is None:
+            print('Warning! No saved model found.')
+            return False
+        self.best_s2ag_loss_epoch, self.best_s2ag_loss = e, l
+        loaded = torch.load(os.path.join(self.args.work_dir_s2ag, name), map_location=self.device)
+        self.s2ag_generator.load_state_dict(loaded['gen_model_dict'])
+        self.s2ag_discriminator.load_state_dict(loaded['dis_model_dict'])
+        return True
+
+    def load_trimodal(self):
+        path = os.path.join(self.base_path, 'outputs', 'trimodal_gen.pth.tar')
+        if os.path.exists(path):
+            ck = torch.load(path, map_location=self.device)
+            self.trimodal_generator.load_state_dict(ck['trimodal_gen_dict'])
+            return True
+        return False  # synthetic runs: random-init frozen baseline
+
+    def train(self):
+        self.load_trimodal()
+        start = 0
+        if getattr(self.args, "s2ag_load_last_best", False) and self.load_model_at_epoch(self.args.s2ag_start_epoch):
+            start = self.best_s2ag_loss_epoch
+        for epoch in range(start, self.args.s2ag_num_epoch):
+            self.meta_info['epoch'] = epoch
+            self.io.print_log('s2ag training epoch: {}'.format(epoch))
+            self.per_train_epoch()
+            if epoch % self.args.val_interval == 0 or epoch + 1 == self.args.s2ag_num_epoch:
+                self.io.print_log('s2ag val epoch: {}'.format(epoch))
+                self.per_val_epoch()
+            if self.rank == 0 and (self.s2ag_loss_updated or
+                                   (epoch % self.args.save_interval == 0 and epoch > self.min_train_epochs)):
+                os.makedirs(self.args.work_dir_s2ag, exist_ok=True)
+                torch.save({'gen_model_dict': self.s2ag_generator.state_dict(),
+                            'dis_model_dict': self.s2ag_discriminator.state_dict()},
+                           os.path.join(self.args.work_dir_s2ag, 'epoch_{:06d}_loss_{:.4f}_model.pth.tar'.format(
+                               epoch, self.epoch_info['mean_s2ag_loss'])))
+
+    # ------------------------------------------------------------------ inference entry points
+    def generate_gestures(self, samples_to_generate=10, randomized=True, load_saved_model=True,
+                          s2ag_epoch='best', make_video=False, calculate_metrics=True):
+        """34-frame batched evaluation (processor_v2.py:1071-1142): eval mode, batch 2048, the full
+        step under no_grad.  Returns {'loss': mean L1 ours, 'loss_trimodal': ..., 'clips': n}."""
+        if load_saved_model:
+            assert self.load_model_at_epoch(epoch=s2ag_epoch), 'Speech to emotive gestures model not found'
+            self.load_trimodal()
+        for net in (self.trimodal_generator, self.s2ag_generator, self.s2ag_discriminator):
+            net.eval()
+        batch_size = 2048
+        test = self.data_loader['test_data_s2ag'].samples
+        n = min(samples_to_generate, self.num_test_samples)
+        acc = torch.zeros(2, device=self.device)
+        start_time = time.time()
+        for s in range(0, n, batch_size):
+            keys = np.arange(s, min(n, s + batch_size))
+            if randomized:
+                keys = np.random.choice(self.num_test_samples, size=len(keys), replace=False)
+            text, vec, audio, mfcc, vids = self._gather(test, keys)
+            vids = torch.from_numpy(vids).long().to(self.device)
+            with torch.no_grad():
+                m = self.gan_step_async(text, audio, mfcc, vec, vids, train=False)
+            acc += m[M_L1:M_L1_TRI + 1] * len(keys)
+        l1, l1_tri = (acc / n).tolist()
+        print('[VAL Trimodal]\tloss: {:.3f} / [VAL Ours]\tloss: {:.3f} / {:.1f}s'.format(l1_tri, l1,
+                                                                                         time.time() - start_time))
+        return {'loss': l1, 'loss_trimodal': l1_tri, 'clips': n}
+
+    @torch.no_grad()
+    def synthesize_long_form(self, text_chunks, mfcc_chunks, audio_chunks, vid_indices, seed_poses=None,
+                             run_trimodal=False):
+        """Lock-step batched version of render_clip's chunked autoregression (processor_v2.py:1200-1331):
+        every clip of the batch advances one 34-frame chunk at a time (stride 30); the last
+        n_pre_poses frames of a chunk seed the next (:1282-1290) and the overlap is blended linearly,
+        out[j] = prev[j]*(n-j)/(n+1) + next[j]*(j+1)/(n+1) (:1303-1327) -- all on the device.
+          text_chunks [B, n_chunks, 34] int64; mfcc_chunks [B, n_chunks, 37, 71]; audio_chunks
+          [B, n_chunks, audio_len] (only read when run_trimodal); vid_indices [B].
+        Returns dir-vec sequence [B, 34 + 30*(n_chunks-1), pose_dim]."""
+        G = self.s2ag_generator
+        G.eval()
+        self.trimodal_generator.eval()
+        B, n_chunks = text_chunks.shape[0], text_chunks.shape[1]
+        T, P, n_pre = self.time_steps, self.pose_dim, self.s2ag_config_args.n_pre_poses
+        stride = T - n_pre
+        total = T + stride * (n_chunks - 1)
+        result = torch.zeros(B, total, P, device=self.device)
+        pre_seq = torch.zeros(B, T, P + 1, device=self.device)
+        if seed_poses is not None:
+            pre_seq[:, :n_pre, :-1] = seed_poses[:, :n_pre]
+            pre_seq[:, :n_pre, -1] = 1
+        w_next = (torch.arange(n_pre, device=self.device, dtype=torch.float32) + 1) / (n_pre + 1)
+        w_prev = 1.0 - w_next
+        for c in range(n_chunks):
+            if c > 0:
+                pre_seq.zero_()
+                pre_seq[:, :n_pre, :-1] = out[:, -n_pre:]
+                pre_seq[:, :n_pre, -1] = 1
+            if run_trimodal:
+                self.trimodal_generator(pre_seq, text_chunks[:, c], audio_chunks[:, c], vid_indices)
+            out, *_ = G(pre_seq, text_chunks[:, c], mfcc_chunks[:, c], vid_indices)
+            s = c * stride
+            if c == 0:
+                result[:, :T] = out
+            else:
+                ov = result[:, s:s + n_pre]
+                result[:, s:s + n_pre] = ov * w_prev[None, :, None] + out[:, :n_pre] * w_next[None, :, None]
+                result[:, s + n_pre:s + T] = out[:, n_pre:]
+        return result

@@ -53,6 +53,21 @@ def test_linear_into_slice(dev):
     close(xd.grad, g[:, :, 4:12] @ w, what="dx")
 
 
+def test_linear_t(dev):
+    torch.manual_seed(21)
+    B, L, C, N = 5, 37, 34, 32
+    x, w, b = torch.randn(B, L, C), torch.randn(N, L), torch.randn(N)
+    xr, wr, br = P(x, "cpu"), P(w, "cpu"), P(b, "cpu")
+    ref = F.leaky_relu(F.linear(xr.transpose(1, 2), wr, br), 0.3)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xd, wd, bd = P(x, dev), P(w, dev), P(b, dev)
+    buf = torch.zeros(B, C, 40, device=dev)
+    y = ops.linear_t(xd, wd, bd, ops.ACT_LEAKY, 0.3, out=ops.col_slice(buf, 8, 40))
+    y.backward(g.to(dev))
+    close(y, ref); close(xd.grad, xr.grad, what="dx"); close(wd.grad, wr.grad, what="dw"); close(bd.grad, br.grad)
+
+
 CONV1D = [  # L, Cin, Cout, k, s, p, d
     (37, 71, 64, 5, 1, 2, 1), (37, 48, 34, 3, 1, 1, 1), (200, 1, 16, 15, 5, 30, 1), (120, 16, 32, 15, 6, 0, 1),
     (34, 27, 16, 3, 1, 0, 1),
@@ -253,7 +268,6 @@ def test_bigru(dev, In, H, sum_halves):
                       "bias_hh_l%d%s" % (l, sfx)]
     ps = [P(getattr(gru, n).detach(), dev) for n in names]
     buf = torch.zeros(B, T, In, device=dev)
-    piece = ops.linear(P(torch.eye(In), dev, False), P(torch.eye(In), dev, False))  # dummy op to satisfy API
     xd = P(x, dev)
     # feed x through an identity Linear into the buffer so that dx flows back through `pieces`
     eye = torch.eye(In, device=dev)
