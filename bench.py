@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full GAN training iteration (processor_v2.py:776-957 semantics:
+D step + G step, forward/backward/Adam, dropout as shipped) over a synthetic TED-shaped batch.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels), one rank per GPU
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU cores
+
+A "step" = one GAN iteration over `--batch-per-gpu` clips per rank (weak scaling: 256 clips/GPU, i.e.
+BASELINE.json's batch-2048 configuration at 8 GPUs).  Prints ONE JSON line (rank 0).
+  value  : clips/s, whole job, inputs resident in HBM, the step replayed as a CUDA graph, CUDA-event timed
+  e2e    : clips/s through the public Processor API with HOST (pinned) inputs: per step H2D of the batch,
+           the graph replay, D2H read of the 8-float loss/metric vector
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace as NS
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_WORDS, N_SPEAKERS, AUDIO_LEN = 20000, 1370, 36267
+FLOP_PER_CLIP = 3.396e9  # reference step, FlopCounterMode
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "bf16_burst": float(d.get("bf16_tflops", 1590.0)),
+                    "bf16_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                    "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+def cfg_namespace():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import s2ag_oracle as O
+    return NS(**O.CFG), O
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+def cpu_reference_clips_per_s(sample_b, steps, warmup, threads):
+    """The reference algorithm (oracle/s2ag_oracle.py restatement; the Python reference itself cannot
+    travel to the GPU box) on the host cores: full GAN iteration, fp32, `threads` torch threads."""
+    import torch
+    cfg, O = cfg_namespace()
+    torch.set_num_threads(threads)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import build_nets, sd_cpu
+    G, T, D, _ = build_nets("full", N_WORDS, N_SPEAKERS, torch.device("cpu"))
+    g_sd, d_sd, t_sd = (O.as_leaves(sd_cpu(n)) for n in (G, D, T))
+    del G, T, D
+    batch, eps_list, rand_idx = O.synthetic_batch(sample_b, N_WORDS, N_SPEAKERS, AUDIO_LEN, 1234)
+    state = {}
+    for _ in range(warmup):
+        O.gan_step(g_sd, d_sd, t_sd, batch, eps_list, rand_idx, O.CFG, state, train=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.gan_step(g_sd, d_sd, t_sd, batch, eps_list, rand_idx, O.CFG, state, train=True)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_b / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = args.cpu_sample_batch
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    v, dt = cpu_reference_clips_per_s(sample_b, steps, warm, threads)
+    line = {
+        "impl": "reference", "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step",
+        "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full GAN step (D+G fwd/bwd+Adam), %d clips/GPU, fp32, n_words=%d" % (
+            args.batch_per_gpu, N_WORDS)},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": "%d timed GAN iterations of %d clips (oracle port of processor_v2.forward_pass_s2ag, "
+                                   "dropout off)" % (steps, sample_b)},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=256)
+    ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from speech2affective_gestures_b200 import _C, ops
+    from speech2affective_gestures_b200.processor_v2 import Processor
+    from speech2affective_gestures_b200.synthetic import make_data_loader, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _C.lib()
+    assert lib.s2ag_is_device_build() == 1, "CUDA extension missing: there is no fallback"
+
+    cfg, O = cfg_namespace()
+    B = args.batch_per_gpu
+    pargs = NS(no_cuda=False, work_dir_s2ag=None, save_log=False, print_log=False, train_s2ag=True, batch_size=B,
+               s2ag_num_epoch=1, val_interval=1, save_interval=10)
+    dl = make_data_loader(8, 8, 8, n_words=N_WORDS, n_speakers=N_SPEAKERS)
+    torch.manual_seed(1234 + rank)
+    ops.manual_seed(1234 + rank)
+    pr = Processor(ROOT, pargs, cfg, dl, 27, 3, 16000)
+    pr.meta_info["epoch"] = 1  # GAN branch active (loss_warmup = 0)
+    for net in (pr.s2ag_generator, pr.s2ag_discriminator):
+        net.train()
+    pr.trimodal_generator.train()  # the reference never calls .eval() on it before train() (processor_v2.py:961-962)
+
+    host = synthetic_batch(B, None, N_WORDS, N_SPEAKERS, AUDIO_LEN, seed=1234 + rank, pin=True)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    host_metrics = torch.zeros(8, dtype=torch.float32).pin_memory()
+
+    use_graph = not args.no_graph
+    n0 = lib.s2ag_launch_count()
+    if use_graph:
+        try:
+            pr.capture_step(B, train=True, warmup=2)
+        except Exception as e:  # e.g. NCCL capture unsupported: run the step eagerly
+            if rank == 0:
+                print("graph capture failed (%s); running eagerly" % str(e)[:200], file=sys.stderr)
+            use_graph = False
+    if not use_graph:
+        pr.static_in = tuple(t.to(dev) for t in host)
+    n1 = lib.s2ag_launch_count()
+    pr.load_static_inputs(*[host[i] for i in (0, 1, 2, 3, 4)]) if use_graph else None
+    torch.cuda.synchronize()
+
+    def one_step():
+        if use_graph:
+            pr.replay_step()
+        else:
+            pr.gan_step_async(*pr.static_in, True)
+
+    c0 = lib.s2ag_launch_count()
+    one_step()
+    launches_per_step = (lib.s2ag_launch_count() - c0) if not use_graph else None
+    if use_graph:  # kernels recorded into the graph by the capture pass (last of the warmup+capture passes)
+        launches_per_step = (n1 - n0) // 3
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    # ---- device-resident timing
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end timing (pinned host inputs -> H2D -> step -> D2H metrics), public Processor API
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pr.load_static_inputs(*host)
+        one_step()
+        host_metrics.copy_(pr.metrics, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms, t_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, t_e2e = tt.tolist()
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (t_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on its launch stream
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        M, N, K = B * 34, 1800, 600  # GRU layer input projection, both directions (gemm_simt_kernel)
+        x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev); y = torch.empty(M, N, device=dev)
+        bias = torch.zeros(N, device=dev)
+        st = ops._stream(x)
+        call = lambda: _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(bias), ops._p(y), N, M, N, K, 0, 0.0, st)
+        for _ in range(3):
+            call()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        reps = 10
+        k0.record()
+        for _ in range(reps):
+            call()
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_simt_kernel (GRU input projection %dx%dx%d, fp32 SIMT)" % (M, N, K),
+                "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
+                "traffic": None, "peak_source": pk["source"], "kernel_ms": kms,
+                "step_frac_of_tensor_roofline": (value / world) * FLOP_PER_CLIP / 1e12 / pk["bf16_sustained"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_reference_clips_per_s(args.cpu_sample_batch, 1, 1, threads)
+        cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": "1 timed GAN iteration of %d clips after 1 warm-up (oracle port of "
+                         "processor_v2.forward_pass_s2ag, dropout off, %d torch threads)" % (args.cpu_sample_batch, threads)}
+
+    if rank == 0:
+        line = {
+            "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step", "value": value,
+            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full GAN step (D step + G step: 3 G fwd, 1 frozen tri-modal fwd incl. WavEncoder, "
+                                   "3 D fwd, G+D bwd, 2 Adam), %d clips/GPU, 34 frames x 27-D, audio %d samples, "
+                                   "10-token text, n_words=%d, dropout as shipped" % (B, AUDIO_LEN, N_WORDS),
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (activations+saved gates+params, >1 GB) exceeds the 126 MB L2; "
+                             "no explicit flush", "cuda_graph": use_graph},
+            "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,
+                    "ms_per_step": t_e2e / args.steps},
+            "gpu_launches": int(launches_per_step * (2 * args.steps)) if launches_per_step else 0,
+            "gpu_launches_per_step": int(launches_per_step or 0),
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,8 @@ const char* s2ag_last_error(void);
 /* 1 when the library was compiled from CUDA sources for sm_100a; the CPU logic-emulation build
  * used by tests/emu reports 0 and is never loaded by the product path. */
 int s2ag_is_device_build(void);
+/* number of kernels this library has launched (or recorded into a graph capture) so far */
+unsigned long long s2ag_launch_count(void);
 
 #define S2AG_ACT_NONE 0
 #define S2AG_ACT_RELU 1

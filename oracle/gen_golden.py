@@ -1,0 +1,205 @@
+"""TEST INFRASTRUCTURE.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported with stubbed third-party modules -- SURVEY Appendix A, recipes A and B)
+on seeded synthetic inputs, and pins oracle/s2ag_oracle.py against it.
+
+Run in the build container (the reference checkout does not exist on the GPU box):
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+De-randomisation: every nn.Dropout p=0 and nn.GRU.dropout=0, re_parametrize replaced
+by an injected-eps version, torch.randperm patched to the injected permutation.  BatchNorm stays
+in train mode.  Weights come from oracle.fill_state_dict (numpy MT19937 => portable), so the
+fixtures hold only inputs' seeds and the reference's OUTPUTS.
+"""
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("S2AG_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+
+class Stub(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        return MagicMock()
+
+
+for n in ['librosa', 'librosa.feature', 'librosa.display', 'lmdb', 'matplotlib', 'matplotlib.pyplot',
+          'matplotlib.ticker', 'matplotlib.animation', 'mpl_toolkits', 'mpl_toolkits.mplot3d',
+          'python_speech_features', 'h5py', 'umap', 'soundfile', 'fasttext', 'transforms3d', 'configargparse',
+          'pyttsx3', 'nltk', 'nltk.corpus']:
+    m = Stub(n)
+    m.__path__ = []
+    sys.modules[n] = m
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+if not torch.cuda.is_available():  # AffEncoder hard-codes .cuda() (net/multimodal_context_net_v2.py:106,115,163)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+import processor_v2 as RP  # noqa: E402  (the reference)
+import net.embedding_net as ren  # noqa: E402
+import net.ser_att_conv_rnn_v2 as ratt  # noqa: E402
+from utils.vocab import Vocab  # noqa: E402
+from types import SimpleNamespace as NS  # noqa: E402
+
+import s2ag_oracle as O  # noqa: E402
+
+N_WORDS, N_SPK, B = 64, 24, 4
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+
+def derand(net):
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.GRU):
+            m.dropout = 0.0
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / max(b.abs().max().item(), 1e-9))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    cfg = NS(**O.CFG)
+    spk = Vocab('vid', insert_default_tokens=False)
+    [spk.index_word('v%d' % i) for i in range(N_SPK)]
+    ctors = (lambda: RP.PoseGenerator(cfg, 27, N_WORDS, 300, None, 71, 37, 34, z_obj=spk),
+             lambda: RP.PGT(cfg, 27, N_WORDS, 300, None, z_obj=spk),
+             lambda: RP.AffDiscriminator(27),
+             lambda: RP.CDT(27))
+    G, T, D, C = (c() for c in ctors)
+    for i, net in enumerate((G, T, D, C)):
+        derand(net)
+        O.fill_state_dict(net.state_dict(), 100 + i)
+
+    def clone(i, net):  # (deepcopy fails on old-style weight_norm modules)
+        n2 = ctors[i]()
+        derand(n2)
+        n2.load_state_dict(net.state_dict())
+        return n2
+
+    def sd_copy(net):
+        return {k: v.detach().clone() for k, v in net.state_dict().items()}
+    batch, eps_list, rand_idx = O.synthetic_batch(B, N_WORDS, N_SPK, 36267, seed=1234)
+    text, audio, mfcc, target, vid = batch
+    pre = target.new_zeros(B, 34, 28)
+    pre[:, :4, :-1] = target[:, :4]
+    pre[:, :4, -1] = 1
+
+    # ---------------- module level (train-mode BN, fresh copies so running stats start equal)
+    fix = {}
+    import copy
+    eps_it = {'i': 0, 'seq': [eps_list[0]]}
+
+    def inj(mu, lv):
+        e = eps_it['seq'][eps_it['i'] % len(eps_it['seq'])]
+        eps_it['i'] += 1
+        return mu + e * torch.exp(0.5 * lv)
+    ren.re_parametrize = inj
+
+    with torch.no_grad():
+        g2, t2, d2, c2 = (clone(i, n) for i, n in enumerate((G, T, D, C)))
+        ro = g2(pre, text, mfcc, vid)
+        oo = O.pose_generator(sd_copy(G), pre, text, mfcc, vid, eps_list[0], True)
+        print("G   oracle vs reference rel err", rel(oo[0], ro[0]))
+        assert rel(oo[0], ro[0]) < 1e-5
+        fix['g_out'], fix['g_z'], fix['g_mu'], fix['g_lv'] = (x.numpy() for x in ro)
+        rt = t2(pre, text, audio, vid)
+        ot = O.pose_generator_trimodal(sd_copy(T), pre, text, audio, vid, eps_list[0], True)
+        print("T   oracle vs reference rel err", rel(ot[0], rt[0]))
+        assert rel(ot[0], rt[0]) < 1e-5
+        fix['t_out'] = rt[0].numpy()
+        rd = d2(target)
+        od = O.aff_discriminator(sd_copy(D), target, True)
+        print("D   oracle vs reference rel err", rel(od, rd))
+        assert rel(od, rd) < 1e-5
+        fix['d_out'] = rd.numpy()
+        rc = c2(target)
+        oc = O.conv_discriminator(sd_copy(C), target, True)
+        print("CD  oracle vs reference rel err", rel(oc, rc))
+        assert rel(oc, rc) < 1e-5
+        fix['c_out'] = rc.numpy()
+        # eval-mode generator (running stats as filled)
+        g3 = clone(0, G).eval()
+        eps_it['i'] = 0
+        fix['g_out_eval'] = g3(pre, text, mfcc, vid)[0].numpy()
+        oe = O.pose_generator(sd_copy(G), pre, text, mfcc, vid, eps_list[0], False)
+        assert rel(oe[0], torch.from_numpy(fix['g_out_eval'])) < 1e-5
+        # running statistics after one train-mode pass
+        fix['g_rm'] = g2.state_dict()['aff_encoder.batch_norm1.running_mean'].numpy()
+        fix['g_rv'] = g2.state_dict()['audio_encoder.batch_norm4.running_var'].numpy()
+
+    # attention (named off-path): net/ser_att_conv_rnn_v2.py:16-34
+    att = ratt.Attention(32, 32, False)
+    O.fill_state_dict(att.state_dict(), 200, scale=2.0)
+    xa = torch.from_numpy(np.random.RandomState(7).normal(0, 1, size=(3, 150, 32)).astype(np.float32))
+    with torch.no_grad():
+        ao, aa = att(xa)
+        bo, ba = O.attention(xa, att.linear1.weight, att.linear1.bias, att.linear2.weight, att.linear2.bias)
+    assert rel(bo, ao) < 1e-5 and rel(ba, aa) < 1e-5
+    fix['att_out'], fix['att_alpha'] = ao.numpy(), aa.numpy()
+
+    # ---------------- step level: the unmodified Processor.forward_pass_s2ag, two consecutive iterations
+    pr = RP.Processor.__new__(RP.Processor)
+    pr.s2ag_config_args, pr.meta_info, pr.use_mfcc = cfg, dict(epoch=1, iter=0), True
+    pr.trimodal_generator, pr.s2ag_generator, pr.s2ag_discriminator = T, G, D
+    pr.s2ag_gen_optimizer = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    pr.s2ag_dis_optimizer = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight,
+                                             betas=(0.5, 0.999))
+    g_sd, d_sd, t_sd = O.as_leaves(G.state_dict()), O.as_leaves(D.state_dict()), O.as_leaves(T.state_dict())
+    opt_state = {}
+    real_randperm = torch.randperm
+    torch.randperm = lambda n, *a, **k: rand_idx.clone()
+    captured = {}
+    G.register_forward_hook(lambda m, i, o: captured.setdefault('g', []).append(o[0].detach().clone()))
+    T.register_forward_hook(lambda m, i, o: captured.setdefault('t', []).append(o[0].detach().clone()))
+    for it in range(2):
+        captured.clear()
+        eps_it['i'] = 0
+        eps_it['seq'] = eps_list  # G pass 1, T pass, G pass 2, G pass 3
+        ret = pr.forward_pass_s2ag(text, audio, mfcc, target, vid, train=True)[0]
+        ores = O.gan_step(g_sd, d_sd, t_sd, batch, eps_list, rand_idx, O.CFG, opt_state, train=True)
+        out_ref = captured['g'][1]
+        print("step %d: ret ref %.6f oracle %.6f | out rel %.2e" % (it, ret, ores['ret'], rel(ores['out_dir_vec'], out_ref)))
+        assert abs(ret - ores['ret']) < 1e-5 and rel(ores['out_dir_vec'], out_ref) < 1e-4
+        fix['step%d_ret' % it] = np.float32(ret)
+        fix['step%d_out' % it] = out_ref.numpy()
+        fix['step%d_out_tri' % it] = captured['t'][0].numpy()
+        fix['step%d_losses' % it] = np.array([ores[k] for k in ('dis', 'huber', 'gen', 'kld', 'div', 'total')],
+                                             dtype=np.float32)
+    torch.randperm = real_randperm
+    # post-step weights (after two Adam steps): a checksum slice per parameter, G and D
+    for name, net, osd in (('g', G, g_sd), ('d', D, d_sd)):
+        sd = net.state_dict()
+        keys = [k for k in sorted(sd.keys()) if sd[k].dtype.is_floating_point]
+        # Adam turns the fp32 rounding noise of mathematically-zero gradients (conv biases feeding a
+        # BatchNorm) into +-lr updates, so those tensors are compared to 2*lr*steps absolute instead.
+        worst = 0.0
+        for k in keys:
+            r = rel(osd[k].detach(), sd[k])
+            a = float((osd[k].detach() - sd[k]).abs().max())
+            if r > 2e-3:
+                print("   noisy:", k, "rel %.2e abs %.2e" % (r, a))
+                assert a <= 2 * 2 * cfg.learning_rate + 1e-6, k
+            else:
+                worst = max(worst, r)
+        print("post-step %s weights: oracle vs reference worst rel %.2e" % (name, worst))
+        fix['post_%s_head' % name] = np.stack([np.resize(sd[k].flatten()[:8].numpy(), 8) for k in keys])
+        fix['post_%s_sum' % name] = np.array([sd[k].double().sum().item() for k in keys])
+        fix['post_%s_keys' % name] = np.array(keys)
+    fix['meta'] = np.array([N_WORDS, spk.n_words, B, 1234, N_SPK])  # spk.n_words = rows of the speaker table
+    np.savez_compressed(os.path.join(OUT, "s2ag_reference_golden.npz"), **fix)
+    print("wrote", os.path.join(OUT, "s2ag_reference_golden.npz"),
+          os.path.getsize(os.path.join(OUT, "s2ag_reference_golden.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libs2ag_b200.so")
 
 _CT = {
     "int": ctypes.c_int, "long": ctypes.c_long, "float": ctypes.c_float, "uint64_t": ctypes.c_uint64,
-    "void": None, "char*": ctypes.c_char_p,
+    "void": None, "char*": ctypes.c_char_p, "unsignedlonglong": ctypes.c_ulonglong,
 }
 
 

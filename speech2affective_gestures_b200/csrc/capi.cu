@@ -12,6 +12,8 @@ void s2ag_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+unsigned long long g_s2ag_launches = 0;
+extern "C" unsigned long long s2ag_launch_count(void) { return g_s2ag_launches; }
 extern "C" int s2ag_version(void) { return 100; }
 extern "C" const char* s2ag_last_error(void) { return g_err; }
 extern "C" int s2ag_is_device_build(void) {

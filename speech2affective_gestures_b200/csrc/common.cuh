@@ -11,8 +11,12 @@
 #include <cmath>
 #define S2AG_DYN_SMEM(type, name) extern __shared__ __align__(1024) unsigned char s2ag_dyn_smem_raw[]; \
   type* name = reinterpret_cast<type*>(s2ag_dyn_smem_raw)
-#define S2AG_LAUNCH(kfn, grid, block, smem, stream, ...) \
-  kfn<<<dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+extern unsigned long long g_s2ag_launches;
+#define S2AG_LAUNCH(kfn, grid, block, smem, stream, ...)                                                  \
+  do {                                                                                                    \
+    ++g_s2ag_launches;                                                                                    \
+    kfn<<<dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                \
+  } while (0)
 static inline cudaError_t cudaMemcpyAsyncD2D(void* d, const void* s, size_t n, cudaStream_t st) {
   return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st);
 }

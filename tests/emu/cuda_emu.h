@@ -179,5 +179,9 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 
 #define S2AG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::S().dyn_smem)
-#define S2AG_LAUNCH(kfn, grid, block, smem, stream, ...) \
-  emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); })
+extern unsigned long long g_s2ag_launches;
+#define S2AG_LAUNCH(kfn, grid, block, smem, stream, ...)                                  \
+  do {                                                                                    \
+    ++g_s2ag_launches;                                                                    \
+    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); });    \
+  } while (0)

@@ -1,0 +1,167 @@
+"""Module-level parity of the net.multimodal_context_net_v2 mirror against the oracle (and, on the
+GPU, against the fixtures recorded from the unmodified reference).  Tolerance 1e-3 relative
+(north_star), asserted much tighter where fp32 allows."""
+import numpy as np
+import pytest
+import torch
+
+from common import O, GOLDEN, build_nets, sd_cpu, inject_eps, rel, cfg_dict
+
+N_WORDS, N_SPK = 40, 12
+
+
+def _batch(B, n_words=N_WORDS, n_spk=N_SPK, seed=5):
+    batch, eps_list, rand_idx = O.synthetic_batch(B, n_words, n_spk, 36267, seed)
+    text, audio, mfcc, target, vid = batch
+    pre = target.new_zeros(B, 34, 28)
+    pre[:, :4, :-1] = target[:, :4]
+    pre[:, :4, -1] = 1
+    return text, audio, mfcc, target, vid, pre, eps_list, rand_idx
+
+
+def _check_grads(net, osd, tol=2e-3):
+    gmax = max(v.grad.abs().max().item() for v in osd.values() if v.requires_grad and v.grad is not None)
+    for name, p in net.named_parameters():
+        og = osd[name].grad
+        if og is None:
+            continue
+        err = (p.grad.detach().cpu() - og).abs().max().item()
+        assert err <= tol * (og.abs().max().item() + 1e-3 * gmax), "%s: grad err %.3e (ref max %.3e)" % (
+            name, err, og.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["tiny", pytest.param("full", marks=pytest.mark.gpu)])
+def test_generator_fwd_bwd_vs_oracle(dev, kind):
+    if kind == "full" and dev.type != "cuda":
+        pytest.skip("full-width config runs on the GPU")
+    c = cfg_dict(kind)
+    B = 3
+    G, T, D, C = build_nets(kind, N_WORDS, N_SPK, dev)
+    text, audio, mfcc, target, vid, pre, eps_list, _ = _batch(B)
+    osd = O.as_leaves(sd_cpu(G))
+    ref = O.pose_generator(osd, pre, text, mfcc, vid, eps_list[0], True, H=c["hidden_size_s2eg"], n_layers=c["n_layers"])
+    g = torch.from_numpy(np.random.RandomState(1).normal(size=ref[0].shape).astype(np.float32))
+    (ref[0] * g).sum().backward()
+    inject_eps([eps_list[0]])
+    G.train()
+    t = lambda a: a.to(dev)
+    out, z, mu, lv = G(t(pre), t(text), t(mfcc), t(vid))
+    (out * t(g)).sum().backward()
+    assert rel(out, ref[0]) < 1e-4 and rel(z, ref[1]) < 1e-5 and rel(mu, ref[2]) < 1e-5 and rel(lv, ref[3]) < 1e-5
+    _check_grads(G, osd)
+    # BatchNorm running statistics were updated like nn.BatchNorm does
+    msd = G.state_dict()
+    for k in ("aff_encoder.batch_norm1.running_mean", "audio_encoder.batch_norm4.running_var",
+              "aff_encoder.st_gcn2.tcn.3.running_var"):
+        assert rel(msd[k], osd[k]) < 1e-4, k
+    assert int(msd["audio_encoder.batch_norm1.num_batches_tracked"]) == 1
+    # eval mode uses the running statistics
+    G.eval()
+    inject_eps([eps_list[0]])
+    with torch.no_grad():
+        oe = G(t(pre), t(text), t(mfcc), t(vid))[0]
+        re_ = O.pose_generator(osd, pre, text, mfcc, vid, eps_list[0], False, H=c["hidden_size_s2eg"],
+                               n_layers=c["n_layers"])[0]
+    assert rel(oe, re_) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["tiny", pytest.param("full", marks=pytest.mark.gpu)])
+def test_trimodal_and_discriminators_vs_oracle(dev, kind):
+    if kind == "full" and dev.type != "cuda":
+        pytest.skip("full-width config runs on the GPU")
+    c = cfg_dict(kind)
+    B = 2
+    G, T, D, C = build_nets(kind, N_WORDS, N_SPK, dev)
+    text, audio, mfcc, target, vid, pre, eps_list, _ = _batch(B)
+    t = lambda a: a.to(dev)
+    inject_eps([eps_list[1]])
+    with torch.no_grad():
+        ot = T(t(pre), t(text), t(audio), t(vid))[0]
+        rt = O.pose_generator_trimodal(sd_cpu(T), pre, text, audio, vid, eps_list[1], True, H=c["hidden_size"],
+                                       n_layers=c["n_layers"])[0]
+    assert rel(ot, rt) < 1e-4
+    for net, fn in ((D, O.aff_discriminator), (C, O.conv_discriminator)):
+        osd = O.as_leaves(sd_cpu(net))
+        x = target.clone().requires_grad_(True)
+        r = fn(osd, x, True)
+        r.sum().backward()
+        xd = t(target).clone().detach().requires_grad_(True)
+        net.train()
+        o = net(xd)
+        o.sum().backward()
+        assert o.shape == (B, 1) and rel(o, r) < 1e-4
+        assert rel(xd.grad, x.grad) < 2e-3
+        _check_grads(net, osd)
+
+
+@pytest.mark.gpu
+def test_modules_match_reference_fixtures_gpu():
+    """the CUDA path against outputs recorded from the UNMODIFIED reference modules"""
+    from speech2affective_gestures_b200 import _C
+    assert _C.lib().s2ag_is_device_build() == 1 and not _C.is_emulated()
+    dev = torch.device("cuda:0")
+    gold = np.load(GOLDEN)
+    n_words, n_spk_rows, B, seed, n_spk = (int(x) for x in gold["meta"])
+    G, T, D, C = build_nets("full", n_words, n_spk_rows, dev)
+    text, audio, mfcc, target, vid, pre, eps_list, _ = _batch(B, n_words, n_spk, seed)
+    t = lambda a: a.to(dev)
+    with torch.no_grad():
+        inject_eps([eps_list[0]])
+        G.eval()
+        assert rel(G(t(pre), t(text), t(mfcc), t(vid))[0], torch.from_numpy(gold["g_out_eval"])) < 1e-4
+        G.train()
+        inject_eps([eps_list[0]])
+        out, z, mu, lv = G(t(pre), t(text), t(mfcc), t(vid))
+        assert rel(out, torch.from_numpy(gold["g_out"])) < 1e-4 and rel(z, torch.from_numpy(gold["g_z"])) < 1e-5
+        assert rel(G.state_dict()["aff_encoder.batch_norm1.running_mean"], torch.from_numpy(gold["g_rm"])) < 1e-4
+        inject_eps([eps_list[0]])
+        assert rel(T(t(pre), t(text), t(audio), t(vid))[0], torch.from_numpy(gold["t_out"])) < 1e-4
+        assert rel(D(t(target)), torch.from_numpy(gold["d_out"])) < 1e-4
+        assert rel(C(t(target)), torch.from_numpy(gold["c_out"])) < 1e-4
+
+
+def test_state_dict_surface(dev):
+    """keys/shapes of the reference's state_dict incl. the weight_norm aliases"""
+    G, T, D, C = build_nets("tiny", N_WORDS, N_SPK, dev)
+    sd = G.state_dict()
+    for k in ("audio_encoder.conv1.weight", "text_encoder.embedding.weight", "text_encoder.tcn.network.0.conv1.weight_g",
+              "text_encoder.tcn.network.0.net.0.weight_v", "text_encoder.tcn.network.3.net.4.bias" if False else
+              "text_encoder.tcn.network.1.net.4.bias", "aff_encoder.st_gcn1.gcn.conv.weight",
+              "aff_encoder.st_gcn2.tcn.2.weight", "aff_encoder.st_gcn1.residual.1.running_var",
+              "aff_encoder.batch_norm1.num_batches_tracked", "speaker_embedding.0.weight", "speaker_mu.weight",
+              "gru.weight_ih_l0_reverse", "out.0.weight", "out.2.bias"):
+        assert k in sd, k
+    assert sd["aff_encoder.st_gcn1.gcn.conv.weight"].shape == (80, 3, 9, 1)
+    assert sd["aff_encoder.st_gcn2.tcn.2.weight"].shape == (16, 16, 9, 3)
+    assert sd["aff_encoder.batch_norm1.weight"].shape == (144,)
+    assert sd["text_encoder.tcn.network.0.conv1.weight_g"].shape[1:] == (1, 1)
+    assert "A1" not in sd and "aff_encoder.A1" not in sd
+    dsd = D.state_dict()
+    assert dsd["gru.weight_ih_l0"].shape == (192, 8) and dsd["out2.weight"].shape == (1, 34)
+    assert C.state_dict()["out2.weight"].shape == (1, 28)
+    # parameters alias one flat buffer; load_state_dict keeps the aliasing
+    G.load_state_dict(sd)
+    p = next(G.parameters())
+    assert p.data_ptr() >= G.flat_params.data_ptr()
+    assert p.data_ptr() < G.flat_params.data_ptr() + G.flat_params.numel() * 4
+
+
+def test_shape_contract_assertions(dev):
+    """runtime contracts of the reference: vid_indices required when speaker-conditioned"""
+    G, T, D, C = build_nets("tiny", N_WORDS, N_SPK, dev)
+    text, audio, mfcc, target, vid, pre, eps_list, _ = _batch(2)
+    t = lambda a: a.to(dev)
+    with pytest.raises(AssertionError):
+        G(t(pre), t(text), t(mfcc), None)
+
+
+def test_no_cpu_fallback():
+    """the product library refuses CPU tensors unless the test emulator was injected explicitly"""
+    from speech2affective_gestures_b200 import _C, ops
+    was = _C._emulated
+    _C._emulated = False
+    try:
+        with pytest.raises(_C.S2agError):
+            ops._check(torch.zeros(2))
+    finally:
+        _C._emulated = was
