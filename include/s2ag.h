@@ -31,6 +31,8 @@ const char* s2ag_last_error(void);
 int s2ag_is_device_build(void);
 /* number of kernels this library has launched (or recorded into a graph capture) so far */
 unsigned long long s2ag_launch_count(void);
+/* debugging aid: cudaStreamIsCapturing status of `stream` (0 none, 1 active, 2 invalidated, <0 error) */
+int s2ag_stream_capture_status(void* stream);
 
 #define S2AG_ACT_NONE 0
 #define S2AG_ACT_RELU 1

@@ -87,8 +87,24 @@ def is_emulated():
     return _emulated
 
 
+_DEBUG_CAPTURE = os.environ.get("S2AG_DEBUG_CAPTURE") == "1"
+_dbg_state = {"bad": False}
+
+
 def call(name, *args):
     l = lib()
+    if _DEBUG_CAPTURE and not _dbg_state["bad"]:
+        import threading
+        st = l.s2ag_stream_capture_status(args[-1])
+        if st not in (0, 1):
+            _dbg_state["bad"] = True
+            print("[s2ag debug] capture already INVALID (%d) before %s (thread %s)" % (
+                st, name, threading.current_thread().name), flush=True)
     rc = getattr(l, name)(*args)
+    if _DEBUG_CAPTURE and not _dbg_state["bad"]:
+        st = l.s2ag_stream_capture_status(args[-1])
+        if st not in (0, 1):
+            _dbg_state["bad"] = True
+            print("[s2ag debug] capture became INVALID (%d) inside %s" % (st, name), flush=True)
     if rc != 0:
         raise S2agError("%s failed (%d): %s" % (name, rc, l.s2ag_last_error().decode()))

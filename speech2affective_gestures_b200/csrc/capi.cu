@@ -14,6 +14,16 @@ void s2ag_set_error(const char* fmt, ...) {
 
 unsigned long long g_s2ag_launches = 0;
 extern "C" unsigned long long s2ag_launch_count(void) { return g_s2ag_launches; }
+extern "C" int s2ag_stream_capture_status(void* stream) {
+#ifdef S2AG_EMU
+  (void)stream; return 0;
+#else
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaError_t e = cudaStreamIsCapturing((cudaStream_t)stream, &st);
+  if (e != cudaSuccess) { cudaGetLastError(); return -(int)e; }
+  return (int)st;  // 0 none, 1 active, 2 invalidated
+#endif
+}
 extern "C" int s2ag_version(void) { return 100; }
 extern "C" const char* s2ag_last_error(void) { return g_err; }
 extern "C" int s2ag_is_device_build(void) {

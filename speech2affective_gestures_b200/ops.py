@@ -132,7 +132,7 @@ class LinearFn(torch.autograd.Function):
         yr, ldy = _rows(y, N)
         assert yr.data_ptr() == y.data_ptr(), "out must be row-strided"
         _C.call("s2ag_linear_fwd", _p(xr), ldx, _p(w), _p(b), _p(yr), ldy, M, N, K, act, float(slope), _stream(x))
-        ctx.t = (xr, w, y)
+        ctx.t = (xr, w, y.detach())  # detached alias: storing `y` itself would tie ctx <-> output in a cycle
         ctx.cfg = (act, float(slope), M, N, K, ldx, b)
         ctx.xshape = x.shape
         return y
@@ -176,7 +176,7 @@ class LinearTFn(torch.autograd.Function):
         yr, ldy = _rows(y, N)
         assert yr.data_ptr() == y.data_ptr()
         _C.call("s2ag_linear_t_fwd", _p(x), _p(w), _p(b), _p(yr), ldy, B, L, C, N, act, float(slope), _stream(x))
-        ctx.t = (x, w, b, y)
+        ctx.t = (x, w, b, y.detach())
         ctx.cfg = (B, L, C, N, act, float(slope))
         return y
 
@@ -249,7 +249,7 @@ class BnActFn(torch.autograd.Function):
         x2, ldx = _rows(x, C)
         M = x.numel() // C
         y = out.t if out is not None else _empty(x.shape, x)
-        y2, ldy = _rows(y, C)
+        y2, ldy = _rows(y.detach(), C)
         assert y2.data_ptr() == y.data_ptr()
         add2, ldadd = (None, 0) if add is None else _rows(add, C)
         ctx.s = _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2, ldadd, cmap, pmap)
@@ -301,7 +301,7 @@ class ConvBnActFn(torch.autograd.Function):
         M = N * Ho * Wo
         if bn is None:
             y = out.t if out is not None else _empty(oshape, x)
-            y2, ldy = _rows(y, Cout)
+            y2, ldy = _rows(y.detach(), Cout)
             _C.call("s2ag_conv_fwd", _p(x2), ldx, N, H, W, Cin, _p(w), _p(b), _p(y2), ldy, Cout, KH, KW, sh, sw, ph,
                     pw, dh, dw, act, float(slope), st)
             ctx.s = None
@@ -311,7 +311,7 @@ class ConvBnActFn(torch.autograd.Function):
             _C.call("s2ag_conv_fwd", _p(x2), ldx, N, H, W, Cin, _p(w), _p(b), _p(c), Cout, Cout, KH, KW, sh, sw, ph, pw,
                     dh, dw, ACT_NONE, 0.0, st)
             y = out.t if out is not None else _empty(oshape, x)
-            y2, ldy = _rows(y, Cout)
+            y2, ldy = _rows(y.detach(), Cout)
             ctx.s = _bn_forward(c, Cout, M, Cout, bn, training, act, slope, y2, ldy, None, 0, cmap, pmap)
         assert y2.data_ptr() == y.data_ptr()
         ctx.bn = bn
@@ -466,7 +466,7 @@ class TcnBlockFn(torch.autograd.Function):
         nonce = seed_nonce(x.device) if p > 0 else None
         _C.call("s2ag_tcn_block_fwd", _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y1), _p(y2), _p(out), B, T, C, dilation,
                 float(p), ctypes.c_uint64(seed), _p(nonce), st)
-        ctx.t = (x, y1, y2, out, w1, w2, n1, n2, v1, g1, b1, v2, g2, b2)
+        ctx.t = (x, y1, y2, out.detach(), w1, w2, n1, n2, v1, g1, b1, v2, g2, b2)
         ctx.cfg = (B, T, C, k, dilation, float(p))
         return out
 
@@ -523,7 +523,7 @@ class BiGruFn(torch.autograd.Function):
             gates = _empty((B * T * 2 * 4 * H,), x) if need_bwd else None
             _C.call("s2ag_gru_layer_fwd", _p(cur), ldcur, _p(wif), _p(wir), _p(bif), _p(bir), _p(whf), _p(whr), _p(bhf),
                     _p(bhr), _p(gi_ws), _p(out), _p(gates), B, T, In, H, st)
-            rec = {"x": cur, "ldx": ldcur, "In": In, "out": out, "gates": gates, "drop": None}
+            rec = {"x": cur, "ldx": ldcur, "In": In, "out": out.detach(), "gates": gates, "drop": None}
             nxt = out
             if training and p > 0 and l < nlayers - 1:
                 seed = next_seed()
@@ -533,7 +533,7 @@ class BiGruFn(torch.autograd.Function):
                 rec["drop"] = (float(p), seed, nonce)
             layers.append(rec)
             cur, ldcur, In = nxt, 2 * H, 2 * H
-        last = layers[-1]["out"]
+            last = out  # (ctx keeps a detached alias; the returned tensor must be a distinct object)
         if sum_halves:
             y = _empty((B, T, H), x)
             _C.call("s2ag_add_halves", _p(last), _p(y), B * T, H, st)
@@ -640,7 +640,7 @@ class DHeadFn(torch.autograd.Function):
         lin1 = _empty((B, T), g)
         out = _empty((B, 1), g)
         _C.call("s2ag_dhead_fwd", _p(g), _p(w1), _p(b1), _p(w2), _p(b2), _p(lin1), _p(out), B, T, H, _stream(g))
-        ctx.t = (g, lin1, out, w1, b1, w2, b2)
+        ctx.t = (g, lin1, out.detach(), w1, b1, w2, b2)
         return out
 
     @staticmethod

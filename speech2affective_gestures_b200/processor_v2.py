@@ -213,8 +213,10 @@ class Processor(object):
         use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
         if use_div:
             if cfg.z_type == 'speaker':
+                # torch.randperm(B) of processor_v2.py:903; drawn as argsort(uniform) on the device so that
+                # the draw is capturable in a CUDA graph (CUDA randperm synchronises the host)
                 rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
-                    torch.randperm(vid_indices.shape[0], device=vid_indices.device)
+                    torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
                 rand_vids = vid_indices[rand_idx]
             else:
                 rand_vids = None
@@ -278,6 +280,8 @@ class Processor(object):
                 self.gan_step_async(*self.static_in, train)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        import gc
+        gc.collect()  # no autograd graph of the warm-up passes may survive into the capture
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self.gan_step_async(*self.static_in, train)

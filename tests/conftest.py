@@ -24,9 +24,14 @@ def dev(request):
     from speech2affective_gestures_b200 import _C
     if request.param == "cuda":
         assert torch.cuda.is_available(), "gpu-marked test needs a CUDA device"
+        if _C.is_emulated():  # never let an earlier emulator injection leak into a GPU test
+            _C._lib, _C._emulated = None, False
         assert _C.lib().s2ag_is_device_build() == 1
         assert not _C.is_emulated()
         return torch.device("cuda:0")
+    cs = getattr(request.node, "callspec", None)
+    if cs is not None and cs.params.get("kind") == "full":
+        pytest.skip("full-width configuration runs on the GPU only")
     if _EMU["lib"] is None:
         sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
         import build_emu

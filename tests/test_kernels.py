@@ -388,3 +388,44 @@ def test_attention(dev):
     t = lambda a: a.detach().to(dev)
     out, al = ops.attention(t(x), t(l1.weight), t(l1.bias), t(l2.weight), t(l2.bias))
     close(out, ref); close(al, alphas)
+
+
+def test_no_reference_cycles(dev):
+    """An op's output must die by reference counting alone: a ctx <-> output cycle keeps the autograd
+    graph (and its AccumulateGrad nodes, bound to the warm-up stream) alive until the cyclic GC runs,
+    which breaks CUDA-graph capture of the backward pass and leaks activations."""
+    import gc
+    import weakref
+    torch.manual_seed(30)
+    B, T, C, H = 2, 34, 8, 6
+    x = P(torch.randn(B, T, C), dev)
+    w, b = P(torch.randn(5, C), dev), P(torch.randn(5), dev)
+    bn = nn.BatchNorm1d(5).to(dev)
+    conv = nn.Conv1d(C, 5, 3, padding=1).to(dev)
+    tp = [P(torch.randn(C, C, 2), dev), P(torch.rand(C, 1, 1) + 0.5, dev), P(torch.randn(C), dev),
+          P(torch.randn(C, C, 2), dev), P(torch.rand(C, 1, 1) + 0.5, dev), P(torch.randn(C), dev)]
+    gp = [P(torch.randn(s) * 0.3, dev) for s in [(3 * H, C), (3 * H, H), (3 * H,), (3 * H,)] * 2]
+    hw = [P(torch.randn(1, H), dev), P(torch.randn(1), dev), P(torch.randn(1, T), dev), P(torch.randn(1), dev)]
+    buf = torch.zeros(B, T, 16, device=dev)
+    makers = {
+        "linear": lambda: ops.linear(x, w, b, ops.ACT_LEAKY, 0.3),
+        "linear_out": lambda: ops.linear(x, w, b, ops.ACT_LEAKY, 0.3, out=ops.col_slice(buf, 0, 5)),
+        "linear_t": lambda: ops.linear_t(x, P(torch.randn(4, T), dev), None, ops.ACT_LEAKY, 0.3),
+        "conv_bn_act": lambda: ops.conv_bn_act(x, conv.weight, conv.bias, (1, 1, 1, 0, 1, 1), bn, ops.ACT_LEAKY, 0.3),
+        "conv_act": lambda: ops.conv_bn_act(x, conv.weight, conv.bias, (1, 1, 1, 0, 1, 1), None, ops.ACT_LEAKY, 0.3),
+        "bn_act": lambda: ops.bn_act(ops.linear(x, w, b), bn, ops.ACT_RELU),
+        "tcn": lambda: ops.tcn_block(x, *tp, 2, 0.0, False),
+        "bigru": lambda: ops.bigru(x, gp, 1, H, 0.0, False),
+        "bigru_sum": lambda: ops.bigru(x, gp, 1, H, 0.0, False, sum_halves=True),
+        "dhead": lambda: ops.dhead(ops.bigru(x, gp, 1, H, 0.0, False), *hw),
+    }
+    gc.collect()
+    gc.disable()
+    try:
+        for name, mk in makers.items():
+            y = mk()
+            r = weakref.ref(y)
+            del y
+            assert r() is None, "reference cycle through the output of %s" % name
+    finally:
+        gc.enable()
