@@ -34,6 +34,16 @@ unsigned long long s2ag_launch_count(void);
 /* debugging aid: cudaStreamIsCapturing status of `stream` (0 none, 1 active, 2 invalidated, <0 error) */
 int s2ag_stream_capture_status(void* stream);
 
+/* Dense-contraction engine: 0 = auto (tcgen05 tensor-core kernel wherever a 128 x BN tile is worthwhile,
+ * exact-fp32 SIMT kernel for tiny shapes), 1 = SIMT everywhere (A/B parity checks). */
+int s2ag_set_engine(int engine);
+/* Tensor-core operand precision: 0 = "bf16x3" (fp32 operands split hi+lo on the fly, three MMAs, fp32
+ * accumulate in TMEM: fp32-grade results, the default and the parity configuration), 1 = "bf16x1"
+ * (single bf16 pass, BASELINE config 3). */
+int s2ag_set_precision(int mode);
+/* bring-up aid for the tcgen05 kernels (bit 0: swap LBO/SBO of the shared-memory descriptors) */
+int s2ag_debug_flags(int flags);
+
 #define S2AG_ACT_NONE 0
 #define S2AG_ACT_RELU 1
 #define S2AG_ACT_LEAKY 2

@@ -13,6 +13,31 @@ void s2ag_set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_s2ag_launches = 0;
+namespace s2ag {
+int g_engine = 0;
+#ifndef S2AG_EMU
+namespace umma { int g_precision = 0; int g_dbg_flags = 0; }
+#endif
+}  // namespace s2ag
+extern "C" int s2ag_set_engine(int engine) {
+  if (engine < 0 || engine > 1) { s2ag_set_error("s2ag_set_engine: engine must be 0 (auto) or 1 (SIMT)"); return S2AG_ERR_ARG; }
+  s2ag::g_engine = engine;
+  return S2AG_OK;
+}
+extern "C" int s2ag_set_precision(int mode) {
+  if (mode < 0 || mode > 1) { s2ag_set_error("s2ag_set_precision: mode must be 0 (bf16x3) or 1 (bf16x1)"); return S2AG_ERR_ARG; }
+#ifndef S2AG_EMU
+  s2ag::umma::g_precision = mode;
+#endif
+  return S2AG_OK;
+}
+extern "C" int s2ag_debug_flags(int flags) {
+#ifndef S2AG_EMU
+  s2ag::umma::g_dbg_flags = flags;
+#endif
+  (void)flags;
+  return S2AG_OK;
+}
 extern "C" unsigned long long s2ag_launch_count(void) { return g_s2ag_launches; }
 extern "C" int s2ag_stream_capture_status(void* stream) {
 #ifdef S2AG_EMU

@@ -2,7 +2,7 @@
 // helpers around them.  Replaces the nn.Linear / nn.Conv1d / nn.Conv2d call sites listed in
 // include/s2ag.h.  All fp32, exact-order-independent up to fp32 summation order.
 #include "s2ag.h"
-#include "gemm_simt.cuh"
+#include "gemm.cuh"
 
 using namespace s2ag;
 

@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(GTHREADS) gemm_simt_kernel(LdA a, LdB b, Epi e
 
 // Host-side launcher.  splitk > 1 requires a linear epilogue (it will atomicAdd partial sums).
 template <class LdA, class LdB, class Epi>
-static inline void launch_gemm(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
-                               void* stream) {
+static inline void launch_gemm_simt(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch,
+                                    int splitk, void* stream) {
   if (M <= 0 || N <= 0) return;
   if (splitk < 1) splitk = 1;
   auto kfn = &gemm_simt_kernel<LdA, LdB, Epi>;

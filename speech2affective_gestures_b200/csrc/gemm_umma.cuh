@@ -1,0 +1,304 @@
+// tcgen05 (UMMA) tiled contraction  C[m,n] = epi( sum_k A(m,k) * B(n,k) )  for sm_100a, with the same
+// pluggable operand loaders / epilogues as the SIMT engine in gemm_simt.cuh, which it replaces
+// for every dense shape of the hot path (GRU input projections, TCN conv-as-GEMM, Conv1d/2d
+// implicit GEMM, linear heads, weight-gradient contractions).
+//
+// Numerics.  The reference computes in fp32 and the parity bar is 1e-3 relative on losses and
+// poses (1e-4 in the module tests), which single-pass bf16 does not meet (4.5e-3).  The
+// operands therefore stay fp32 in HBM and are split ON THE FLY while they are staged into shared
+// memory:  x = hi + lo,  hi = bf16(x),  lo = bf16(x - hi)  (x - hi is exact in fp32), and the
+// tensor core accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  in fp32 in TMEM ("bf16x3", ~2^-17
+// relative operand error).  precision mode 1 ("bf16x1") drops the two correction terms.
+//
+// Structure of one CTA (256 threads, one 128 x BN output tile, BN <= 128 a multiple of 16):
+//   - all 8 warps stage: global -> registers (next k-block prefetched while the current one is
+//     converted) -> bf16 hi/lo -> shared memory in the canonical no-swizzle K-major UMMA layout
+//     [k-chunk of 8][row][16 B], two stages;
+//   - fence.proxy.async + __syncthreads, then ONE thread issues the tcgen05.mma instructions of the
+//     stage (M=128, N=BN, K=16 each) and tcgen05.commit's the stage's "empty" mbarrier, so the
+//     tensor core works on stage s while the warps stage s^1;
+//   - accumulator: BN fp32 columns x 128 lanes of TMEM; epilogue: tcgen05.ld (32 lanes x 32
+//     columns per warp), transposed through shared memory so that global stores (and the
+//     epilogue's bias / residual loads) are coalesced along n.
+// grid = (tilesN, tilesM, nbatch*splitk) exactly like the SIMT engine.
+#pragma once
+#include "gemm_simt.cuh"
+#ifndef S2AG_EMU
+#include <cuda_bf16.h>
+
+namespace s2ag {
+namespace umma {
+
+constexpr int BM = 128, BK = 32, THREADS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2 * 2;  // hi + lo, bf16
+constexpr int HEADER_BYTES = 128;               // mbarriers + TMEM base slot
+
+extern int g_precision;   // 0 = bf16x3 (fp32-grade, default), 1 = bf16x1
+extern int g_dbg_flags;   // bring-up aid: bit0 swaps LBO/SBO in the shared-memory descriptors
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded spin: a protocol bug traps (launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; bf16 inputs, fp32 accumulate, M=128, N and majors from idesc
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` receives row (lane_base + lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle.  Canonical layout (16-byte units):
+// ((8 rows, n groups), 2 k-chunks) : ((1, SBO), LBO)  -- cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::K>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version 1 (sm_100); layout_type (bits 61-63) = 0: no swizzle
+  return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n  (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// 16 consecutive-k fp32 values of one operand row -> bf16 hi (and lo) -> two 16-byte k-chunks
+__device__ __forceinline__ void split_store(const float (&v)[16], unsigned char* hi_base, unsigned char* lo_base,
+                                            int rows, int row, int khalf, bool x3) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float x0 = v[c * 8 + 2 * p], x1 = v[c * 8 + 2 * p + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+      const float r0 = x0 - __low2float(hh), r1 = x1 - __high2float(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+      l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const int off = ((khalf * 2 + c) * rows + row) * 16;
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (x3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <class Ld>
+__device__ __forceinline__ void fetch16(const Ld& ld, int batch, int row, int row_lim, int k, int kend, float (&v)[16]) {
+  if (row < row_lim) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (k + i < kend) ? ld(batch, row, k + i) : 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  }
+}
+
+template <class LdA, class LdB, class Epi>
+__global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi epi, int M, int N, int K, int splitk,
+                                                            int BN, int x3, int dbg) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_empty[2] = {sbase, sbase + 8};
+  const uint32_t bar_done = sbase + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 24);
+  const int b_half_bytes = BN * BK * 2;  // one of hi / lo
+  const int stage_bytes = A_STAGE_BYTES + 2 * b_half_bytes;
+  unsigned char* stage0 = smem + HEADER_BYTES;
+
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int batch = blockIdx.z / splitk, ks = blockIdx.z % splitk;
+  int kper = (K + splitk - 1) / splitk;
+  kper = ((kper + BK - 1) / BK) * BK;
+  const int kbeg = ks * kper;
+  const int kend = (kbeg + kper < K) ? kbeg + kper : K;
+  const int nkb = kbeg < kend ? (kend - kbeg + BK - 1) / BK : 0;
+  const uint32_t ncols = BN <= 32 ? 32u : (BN <= 64 ? 64u : 128u);
+
+  if (tid == 0) {
+    mbar_init(bar_empty[0], 1);
+    mbar_init(bar_empty[1], 1);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(sbase + 24, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // staging assignment: one A item and (at most) one B item of 16 consecutive k per thread
+  const int rowA = tid & (BM - 1), khalfA = tid >> 7;
+  const bool hasB = tid < 2 * BN;
+  const int rowB = hasB ? tid % BN : 0, khalfB = hasB ? tid / BN : 0;
+
+  float va[16], vb[16], na[16], nb[16];
+  if (nkb > 0) {
+    fetch16(a, batch, m0 + rowA, M, kbeg + khalfA * 16, kend, va);
+    if (hasB) fetch16(b, batch, n0 + rowB, N, kbeg + khalfB * 16, kend, vb);
+  }
+  const uint32_t idesc = make_idesc(BN);
+  const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    const bool more = kb + 1 < nkb;
+    if (more) {  // prefetch the next k-block into the second register set
+      const int k0 = kbeg + (kb + 1) * BK;
+      fetch16(a, batch, m0 + rowA, M, k0 + khalfA * 16, kend, na);
+      if (hasB) fetch16(b, batch, n0 + rowB, N, k0 + khalfB * 16, kend, nb);
+    }
+    if (kb >= 2) mbar_wait(bar_empty[s], (uint32_t)(((kb >> 1) - 1) & 1));  // MMAs that read stage s are done
+    unsigned char* st = stage0 + s * stage_bytes;
+    split_store(va, st, st + BM * BK * 2, BM, rowA, khalfA, x3 != 0);
+    if (hasB) split_store(vb, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, BN, rowB, khalfB, x3 != 0);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sa = smem_u32(st), sb = sa + A_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint32_t a_hi = sa + j * 2 * a_lbo, a_lo = a_hi + BM * BK * 2;
+        const uint32_t b_hi = sb + j * 2 * b_lbo, b_lo = b_hi + b_half_bytes;
+        const bool sw = dbg & 1;
+        const uint64_t dah = sw ? make_desc(a_hi, sbo, a_lbo) : make_desc(a_hi, a_lbo, sbo);
+        const uint64_t dbh = sw ? make_desc(b_hi, sbo, b_lbo) : make_desc(b_hi, b_lbo, sbo);
+        uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+        if (x3) {
+          const uint64_t dal = sw ? make_desc(a_lo, sbo, a_lbo) : make_desc(a_lo, a_lbo, sbo);
+          const uint64_t dbl = sw ? make_desc(b_lo, sbo, b_lbo) : make_desc(b_lo, b_lbo, sbo);
+          mma_bf16(tmem_base, dal, dbh, idesc, acc);
+          mma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          acc = 1u;
+        }
+        mma_bf16(tmem_base, dah, dbh, idesc, acc);
+      }
+      mma_commit(bar_empty[s]);
+      if (!more) mma_commit(bar_done);
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { va[i] = na[i]; vb[i] = nb[i]; }
+    }
+  }
+
+  if (nkb > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    // epilogue: the stage buffers are free now (every MMA has completed); reuse them for the transposition
+    float* tbuf = reinterpret_cast<float*>(stage0) + warp * (32 * 33);
+    const int lane_base = (warp & 3) * 32;
+    for (int c0 = (warp >> 2) * 32; c0 < BN; c0 += 64) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      const bool n_ok = (c0 + lane < BN) && n < N;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + lane_base + rr;
+        if (m < M && n_ok) epi(batch, m, n, tbuf[rr * 33 + lane], splitk > 1);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+static inline int pick_bn(int N) {
+  int tiles = (N + 127) / 128;
+  int bn = (N + tiles - 1) / tiles;
+  bn = ((bn + 15) / 16) * 16;
+  if (bn < 16) bn = 16;
+  if (bn > 128) bn = 128;
+  return bn;
+}
+static inline size_t smem_bytes(int BN) {
+  size_t stages = 2 * (size_t)(A_STAGE_BYTES + 2 * BN * BK * 2);
+  size_t epi = 8 * 32 * 33 * sizeof(float);
+  return HEADER_BYTES + (stages > epi ? stages : epi);
+}
+
+template <class LdA, class LdB, class Epi>
+static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
+                          void* stream) {
+  auto kfn = &gemm_umma_kernel<LdA, LdB, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128));
+    attr_set = true;
+  }
+  const int BN = pick_bn(N);
+  dim3 grid(s2ag_cdiv(N, BN), s2ag_cdiv(M, BM), nbatch * splitk);
+  S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0,
+              g_dbg_flags);
+}
+
+// shapes worth a tensor-core tile: anything else stays on the exact-fp32 SIMT kernel
+static inline bool worthwhile(int M, int N, int K) { return M >= 64 && N >= 16 && K >= 32; }
+
+}  // namespace umma
+}  // namespace s2ag
+#endif  // !S2AG_EMU

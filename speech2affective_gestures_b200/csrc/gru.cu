@@ -8,7 +8,7 @@
 // directions in the same launch, grid.z).  Backward mirrors it: per step a gate-gradient kernel
 // and a dh += dGh @ W_hh GEMM, then four time-batched weight-gradient GEMMs.
 #include "s2ag.h"
-#include "gemm_simt.cuh"
+#include "gemm.cuh"
 
 using namespace s2ag;
 namespace s2ag { void launch_colsum(const float* dy, long ld, float* db, int M, int N, void* stream); }

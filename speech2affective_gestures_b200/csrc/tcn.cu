@@ -4,7 +4,7 @@
 // The chomped (acausal) columns the reference computes and discards (tcn.py:12-13) are never
 // computed here, and the two taps are gathered by the operand loader, so no padded copy exists.
 #include "s2ag.h"
-#include "gemm_simt.cuh"
+#include "gemm.cuh"
 
 using namespace s2ag;
 namespace s2ag { void launch_colsum(const float* dy, long ld, float* db, int M, int N, void* stream); }
