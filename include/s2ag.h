@@ -41,7 +41,7 @@ int s2ag_set_engine(int engine);
  * accumulate in TMEM: fp32-grade results, the default and the parity configuration), 1 = "bf16x1"
  * (single bf16 pass, BASELINE config 3). */
 int s2ag_set_precision(int mode);
-/* bring-up aid for the tcgen05 kernels (bit 0: swap LBO/SBO of the shared-memory descriptors) */
+/* reserved for bring-up experiments of the tcgen05 kernels */
 int s2ag_debug_flags(int flags);
 
 #define S2AG_ACT_NONE 0

@@ -22,6 +22,18 @@ struct LdPlain {
   __device__ __forceinline__ float operator()(int b, int row, int k) const {
     return __ldg(p + b * bstride + (long)row * ld_row + (long)k * ld_k);
   }
+  // 4 consecutive k (zero beyond kend); one 16-byte load when k is the contiguous axis and the address is aligned
+  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
+    const float* q = p + b * bstride + (long)row * ld_row + (long)k * ld_k;
+    if (KCONTIG && k + 4 <= kend && ld_k == 1 && (reinterpret_cast<unsigned long long>(q) & 15ull) == 0)
+      return __ldg(reinterpret_cast<const float4*>(q));
+    float4 r;
+    r.x = k < kend ? __ldg(q) : 0.f;
+    r.y = k + 1 < kend ? __ldg(q + ld_k) : 0.f;
+    r.z = k + 2 < kend ? __ldg(q + 2 * ld_k) : 0.f;
+    r.w = k + 3 < kend ? __ldg(q + 3 * ld_k) : 0.f;
+    return r;
+  }
 };
 
 // Implicit im2col over a channels-last activation x[N][H][W][C] (Conv1d: W == 1).
@@ -46,6 +58,25 @@ struct LdConv {
     if (hi < 0 || hi >= H || wi < 0 || wi >= W) return 0.f;
     return __ldg(x + ((long)(n * H + hi) * W + wi) * ldpix + c);
   }
+  // 4 consecutive k: with the (kh, kw, c) order and C % 4 == 0 they are 4 channels of ONE pixel
+  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
+    if (ORDER == ORDER_KKC && (C & 3) == 0 && k + 4 <= kend) {
+      int wo = row % Wo; int t = row / Wo; int ho = t % Ho; int n = t / Ho;
+      int c = k % C; int t2 = k / C; int kw = t2 % KW; int kh = t2 / KW;
+      int hi = ho * sh + sgn * kh * dh + off_h;
+      int wi = wo * sw + sgn * kw * dw + off_w;
+      if (hi < 0 || hi >= H || wi < 0 || wi >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* q = x + ((long)(n * H + hi) * W + wi) * ldpix + c;
+      if ((reinterpret_cast<unsigned long long>(q) & 15ull) == 0) return __ldg(reinterpret_cast<const float4*>(q));
+      return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    }
+    float4 r;
+    r.x = k < kend ? (*this)(b, row, k) : 0.f;
+    r.y = k + 1 < kend ? (*this)(b, row, k + 1) : 0.f;
+    r.z = k + 2 < kend ? (*this)(b, row, k + 2) : 0.f;
+    r.w = k + 3 < kend ? (*this)(b, row, k + 3) : 0.f;
+    return r;
+  }
 };
 
 // Transposed view of another loader (swap the roles of row and k).
@@ -54,18 +85,34 @@ struct LdT {
   static constexpr bool kContig = !L::kContig;
   L l;
   __device__ __forceinline__ float operator()(int b, int row, int k) const { return l(b, k, row); }
+  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
+    float4 r;
+    r.x = k < kend ? l(b, k, row) : 0.f;
+    r.y = k + 1 < kend ? l(b, k + 1, row) : 0.f;
+    r.z = k + 2 < kend ? l(b, k + 2, row) : 0.f;
+    r.w = k + 3 < kend ? l(b, k + 3, row) : 0.f;
+    return r;
+  }
 };
 
 // Weight view for data-gradient GEMMs: element(row=c_in, k) with k -> (co, kk) [ORDER_CKK] or (kk, co) [ORDER_KKC]
 // offset = co*s_co + c*s_c + kk*s_kk
 template <int ORDER>
 struct LdWdgrad {
-  static constexpr bool kContig = true;
+  static constexpr bool kContig = false;  // consecutive k are strided in memory; consecutive rows (c_in) are the near axis
   const float* w; int Cout, KK; long s_co, s_c, s_kk;
   __device__ __forceinline__ float operator()(int, int row, int k) const {
     int co, kk;
     if (ORDER == ORDER_CKK) { kk = k % KK; co = k / KK; } else { co = k % Cout; kk = k / Cout; }
     return __ldg(w + co * s_co + row * s_c + kk * s_kk);
+  }
+  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
+    float4 r;
+    r.x = k < kend ? (*this)(b, row, k) : 0.f;
+    r.y = k + 1 < kend ? (*this)(b, row, k + 1) : 0.f;
+    r.z = k + 2 < kend ? (*this)(b, row, k + 2) : 0.f;
+    r.w = k + 3 < kend ? (*this)(b, row, k + 3) : 0.f;
+    return r;
   }
 };
 

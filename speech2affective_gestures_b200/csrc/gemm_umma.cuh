@@ -34,7 +34,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2 * 2;  // hi + lo, bf16
 constexpr int HEADER_BYTES = 128;               // mbarriers + TMEM base slot
 
 extern int g_precision;   // 0 = bf16x3 (fp32-grade, default), 1 = bf16x1
-extern int g_dbg_flags;   // bring-up aid: bit0 swaps LBO/SBO in the shared-memory descriptors
+extern int g_dbg_flags;   // reserved for bring-up experiments
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -119,41 +119,52 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// 16 consecutive-k fp32 values of one operand row -> bf16 hi (and lo) -> two 16-byte k-chunks
-__device__ __forceinline__ void split_store(const float (&v)[16], unsigned char* hi_base, unsigned char* lo_base,
-                                            int rows, int row, int khalf, bool x3) {
+// 8 consecutive-k fp32 values of one operand row -> bf16 hi (and lo) -> one 16-byte k-chunk each
+__device__ __forceinline__ void split_store(const float (&v)[8], unsigned char* hi_base, unsigned char* lo_base,
+                                            int off, bool x3) {
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const float x0 = v[c * 8 + 2 * p], x1 = v[c * 8 + 2 * p + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-      h[p] = *reinterpret_cast<const uint32_t*>(&hh);
-      const float r0 = x0 - __low2float(hh), r1 = x1 - __high2float(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-      l[p] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    const int off = ((khalf * 2 + c) * rows + row) * 16;
-    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (x3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  for (int p = 0; p < 4; ++p) {
+    const float x0 = v[2 * p], x1 = v[2 * p + 1];
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+    h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float r0 = x0 - __low2float(hh), r1 = x1 - __high2float(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+    l[p] = *reinterpret_cast<const uint32_t*>(&ll);
   }
+  *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (x3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Staging items.  An item is (row r of the tile, k-chunk k8 of the 32-wide k-block) = 8 fp32 -> one 16-byte chunk.
+//   k-contiguous operands: id -> (r = id / 4, k8 = id % 4): a warp reads 8 rows x 128 contiguous bytes (two
+//     16-byte loads per thread) and stores 4 x 128 conflict-free bytes;
+//   row-contiguous operands (transposed views): id -> (r = id % rows, k8 = id / rows): a warp reads 32
+//     consecutive rows per k (coalesced scalar loads) and stores 512 contiguous bytes.
 template <class Ld>
-__device__ __forceinline__ void fetch16(const Ld& ld, int batch, int row, int row_lim, int k, int kend, float (&v)[16]) {
-  if (row < row_lim) {
+__device__ __forceinline__ void item_coords(int id, int rows, int& r, int& k8) {
+  if (Ld::kContig) { r = id >> 2; k8 = id & 3; } else { r = id % rows; k8 = id / rows; }
+}
+template <class Ld>
+__device__ __forceinline__ void fetch_item(const Ld& ld, int batch, int row, int row_lim, int k, int kend,
+                                           float (&v)[8]) {
+  if (row < row_lim && k < kend) {
+    if (Ld::kContig) {
+      const float4 a = ld.load4(batch, row, k, kend), b = ld.load4(batch, row, k + 4, kend);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (k + i < kend) ? ld(batch, row, k + i) : 0.f;
+      for (int i = 0; i < 8; ++i) v[i] = (k + i < kend) ? ld(batch, row, k + i) : 0.f;
+    }
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
   }
 }
 
 template <class LdA, class LdB, class Epi>
 __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi epi, int M, int N, int K, int splitk,
-                                                            int BN, int x3, int dbg) {
+                                                            int BN, int x3) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -185,15 +196,22 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // staging assignment: one A item and (at most) one B item of 16 consecutive k per thread
-  const int rowA = tid & (BM - 1), khalfA = tid >> 7;
-  const bool hasB = tid < 2 * BN;
-  const int rowB = hasB ? tid % BN : 0, khalfB = hasB ? tid / BN : 0;
-
-  float va[16], vb[16], na[16], nb[16];
+  // staging assignment: two A items and (at most) two B items per thread (see item_coords)
+  int rA[2], kA[2], rB[2], kB[2];
+  bool hasB[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    item_coords<LdA>(tid + i * THREADS, BM, rA[i], kA[i]);
+    hasB[i] = tid + i * THREADS < 4 * BN;
+    item_coords<LdB>(hasB[i] ? tid + i * THREADS : 0, BN, rB[i], kB[i]);
+  }
+  float va[2][8], vb[2][8], na[2][8], nb[2][8];
   if (nkb > 0) {
-    fetch16(a, batch, m0 + rowA, M, kbeg + khalfA * 16, kend, va);
-    if (hasB) fetch16(b, batch, n0 + rowB, N, kbeg + khalfB * 16, kend, vb);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      fetch_item(a, batch, m0 + rA[i], M, kbeg + kA[i] * 8, kend, va[i]);
+      if (hasB[i]) fetch_item(b, batch, n0 + rB[i], N, kbeg + kB[i] * 8, kend, vb[i]);
+    }
   }
   const uint32_t idesc = make_idesc(BN);
   const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
@@ -203,13 +221,20 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
     const bool more = kb + 1 < nkb;
     if (more) {  // prefetch the next k-block into the second register set
       const int k0 = kbeg + (kb + 1) * BK;
-      fetch16(a, batch, m0 + rowA, M, k0 + khalfA * 16, kend, na);
-      if (hasB) fetch16(b, batch, n0 + rowB, N, k0 + khalfB * 16, kend, nb);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        fetch_item(a, batch, m0 + rA[i], M, k0 + kA[i] * 8, kend, na[i]);
+        if (hasB[i]) fetch_item(b, batch, n0 + rB[i], N, k0 + kB[i] * 8, kend, nb[i]);
+      }
     }
     if (kb >= 2) mbar_wait(bar_empty[s], (uint32_t)(((kb >> 1) - 1) & 1));  // MMAs that read stage s are done
     unsigned char* st = stage0 + s * stage_bytes;
-    split_store(va, st, st + BM * BK * 2, BM, rowA, khalfA, x3 != 0);
-    if (hasB) split_store(vb, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, BN, rowB, khalfB, x3 != 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      split_store(va[i], st, st + BM * BK * 2, (kA[i] * BM + rA[i]) * 16, x3 != 0);
+      if (hasB[i])
+        split_store(vb[i], st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, (kB[i] * BN + rB[i]) * 16, x3 != 0);
+    }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -219,13 +244,10 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
       for (int j = 0; j < BK / 16; ++j) {
         const uint32_t a_hi = sa + j * 2 * a_lbo, a_lo = a_hi + BM * BK * 2;
         const uint32_t b_hi = sb + j * 2 * b_lbo, b_lo = b_hi + b_half_bytes;
-        const bool sw = dbg & 1;
-        const uint64_t dah = sw ? make_desc(a_hi, sbo, a_lbo) : make_desc(a_hi, a_lbo, sbo);
-        const uint64_t dbh = sw ? make_desc(b_hi, sbo, b_lbo) : make_desc(b_hi, b_lbo, sbo);
+        const uint64_t dah = make_desc(a_hi, a_lbo, sbo), dbh = make_desc(b_hi, b_lbo, sbo);
         uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
         if (x3) {
-          const uint64_t dal = sw ? make_desc(a_lo, sbo, a_lbo) : make_desc(a_lo, a_lbo, sbo);
-          const uint64_t dbl = sw ? make_desc(b_lo, sbo, b_lbo) : make_desc(b_lo, b_lbo, sbo);
+          const uint64_t dal = make_desc(a_lo, a_lbo, sbo), dbl = make_desc(b_lo, b_lbo, sbo);
           mma_bf16(tmem_base, dal, dbh, idesc, acc);
           mma_bf16(tmem_base, dah, dbl, idesc, 1u);
           acc = 1u;
@@ -237,7 +259,9 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
     }
     if (more) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { va[i] = na[i]; vb[i] = nb[i]; }
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { va[i][j] = na[i][j]; vb[i][j] = nb[i][j]; }
     }
   }
 
@@ -292,8 +316,7 @@ static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int
   }
   const int BN = pick_bn(N);
   dim3 grid(s2ag_cdiv(N, BN), s2ag_cdiv(M, BM), nbatch * splitk);
-  S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0,
-              g_dbg_flags);
+  S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0);
 }
 
 // shapes worth a tensor-core tile: anything else stays on the exact-fp32 SIMT kernel

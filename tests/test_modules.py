@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import O, GOLDEN, build_nets, sd_cpu, inject_eps, rel, cfg_dict
+from common import O, GOLDEN, build_nets, sd_cpu, inject_eps, rel, cfg_dict, check_grads
 
 N_WORDS, N_SPK = 40, 12
 
@@ -20,14 +20,8 @@ def _batch(B, n_words=N_WORDS, n_spk=N_SPK, seed=5):
 
 
 def _check_grads(net, osd, tol=2e-3):
-    gmax = max(v.grad.abs().max().item() for v in osd.values() if v.requires_grad and v.grad is not None)
-    for name, p in net.named_parameters():
-        og = osd[name].grad
-        if og is None:
-            continue
-        err = (p.grad.detach().cpu() - og).abs().max().item()
-        assert err <= tol * (og.abs().max().item() + 1e-3 * gmax), "%s: grad err %.3e (ref max %.3e)" % (
-            name, err, og.abs().max().item())
+    ref = {n: v.grad for n, v in osd.items() if v.requires_grad and v.grad is not None}
+    check_grads({n: p.grad for n, p in net.named_parameters() if p.grad is not None}, ref, tol)
 
 
 @pytest.mark.parametrize("kind", ["tiny", pytest.param("full", marks=pytest.mark.gpu)])

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import O, GOLDEN, cfg_dict, derand, sd_cpu, inject_eps, rel
+from common import O, GOLDEN, cfg_dict, derand, sd_cpu, inject_eps, rel, check_grads
 from speech2affective_gestures_b200.processor_v2 import Processor, M_DIS, M_HUBER, M_GEN, M_KLD, M_DIV, M_TOTAL
 from speech2affective_gestures_b200.synthetic import make_data_loader, Vocab
 
@@ -62,12 +62,8 @@ def run_two_steps(pr, c, dev, B, n_words, n_spk, seed, gold=None):
                 for name, net, key in (("G", pr.s2ag_generator, "g_grads"), ("D", pr.s2ag_discriminator, "d_grads")):
                     if name == "D":
                         continue  # D.grad was consumed (and is not recomputed in the G step by design)
-                    og = r[key]
-                    gmax = max(v.abs().max().item() for v in og.values())
-                    for n_, p in net.named_parameters():
-                        if n_ in og:
-                            e = (p.grad.cpu() - og[n_]).abs().max().item()
-                            assert e <= 2e-3 * (og[n_].abs().max().item() + 1e-3 * gmax), (n_, e)
+                    check_grads({n_: p.grad for n_, p in net.named_parameters() if p.grad is not None}, r[key], 2e-3,
+                                what="G grads, iteration 0")
         # post-step weights after two Adam steps (Adam amplifies rounding noise of ~zero gradients to
         # +-lr per step, hence the absolute bound; the bulk must agree tightly)
         lr = c["learning_rate"]

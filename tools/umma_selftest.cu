@@ -122,6 +122,46 @@ int main(int argc, char** argv) {
              [&](int, int m, int k) { return A[(size_t)m * K + k]; }, [&](int, int n, int k) { return B[(size_t)n * K + k]; },
              M, N, K, 1, 1, true);
   }
+  {  // TCN data-gradient: A = gathered dY (sgn=-1), B = weight view W[co][tap][ci] read along co (LdWdgrad)
+    int Bt = 3, T = 34, C = 300, d = 2, M = Bt * T, K = 2 * C;
+    auto G = rnd((size_t)M * C, 11), W = rnd((size_t)C * K, 12, 0.05f);
+    float *dG = dev(G), *dW = dev(W);
+    LdConv<ORDER_KKC> la{dG, T, 1, C, T, 1, 2, 1, 1, 1, d, 1, -1, d, 0, (long)C};
+    LdWdgrad<ORDER_KKC> lb{dW, C, 2, (long)K, 1, (long)C};
+    run_case("tcn dgrad", la, lb,
+             [&](int, int m, int k) { int t = m % T, b = m / T, j = k / C, c = k % C; int ts = t + (1 - j) * d;
+               return (ts < 0 || ts >= T) ? 0.f : G[((size_t)b * T + ts) * C + c]; },
+             [&](int, int n, int k) { int kk = k / C, co = k % C; return W[(size_t)co * K + kk * C + n]; }, M, C, K, 1, 1, false);
+  }
+  {  // TCN weight-gradient: rows co, cols (tap,c), contraction over pixels
+    int Bt = 3, T = 34, C = 300, d = 2, M = Bt * T, K = 2 * C;
+    auto G = rnd((size_t)M * C, 13), X = rnd((size_t)M * C, 14);
+    float *dG = dev(G), *dX = dev(X);
+    LdConv<ORDER_KKC> lx{dX, T, 1, C, T, 1, 2, 1, 1, 1, d, 1, +1, -d, 0, (long)C};
+    int sk = pick_splitk(C, K, M, 1);
+    run_case("tcn wgrad", LdPlain<false>{dG, 1, (long)C, 0}, LdT<LdConv<ORDER_KKC>>{lx},
+             [&](int, int m, int k) { return G[(size_t)k * C + m]; },
+             [&](int, int n, int k) { int t = k % T, b = k / T, j = n / C, c = n % C; int ts = t + (j - 1) * d;
+               return ts < 0 ? 0.f : X[((size_t)b * T + ts) * C + c]; }, C, K, M, 1, sk, false);
+  }
+  {  // unaligned rows (K = 150) and N = 27 (-> BN 32)
+    int M = 8704, N = 27, K = 150;
+    auto A = rnd((size_t)M * K, 15), B = rnd((size_t)N * K, 16);
+    float *dA = dev(A), *dB = dev(B);
+    run_case("linear 150->27 (unaligned)", LdPlain<true>{dA, (long)K, 1, 0}, LdPlain<true>{dB, (long)K, 1, 0},
+             [&](int, int m, int k) { return A[(size_t)m * K + k]; }, [&](int, int n, int k) { return B[(size_t)n * K + k]; },
+             M, N, K, 1, 1, true);
+  }
+  {  // Conv1d implicit GEMM, PyTorch weight order (c, k): MFCC conv1 71->64, k5, pad 2, L=37
+    int Nb = 64, L = 37, Cin = 71, Cout = 64, KH = 5, M = Nb * L, K = Cin * KH;
+    auto X = rnd((size_t)M * Cin, 17), W = rnd((size_t)Cout * K, 18, 0.1f);
+    float *dX = dev(X), *dW = dev(W);
+    LdConv<ORDER_CKK> la{dX, L, 1, Cin, L, 1, KH, 1, 1, 1, 1, 1, +1, -2, 0, (long)Cin};
+    run_case("conv1d 71->64 k5", la, LdPlain<true>{dW, (long)K, 1, 0},
+             [&](int, int m, int k) { int l = m % L, b = m / L, c = k / KH, j = k % KH; int ls = l + j - 2;
+               return (ls < 0 || ls >= L) ? 0.f : X[((size_t)b * L + ls) * Cin + c]; },
+             [&](int, int n, int k) { return W[(size_t)n * K + k]; }, M, Cout, K, 1, 1, true);
+  }
   printf("selftest done\n");
   return 0;
 }
