@@ -156,8 +156,10 @@ int s2ag_embedding_bwd(const int64_t* idx, const float* dout, long ldo, float* d
 
 /* ---- nn.GRU, one bidirectional layer (:480-481,:281-282,:558-560) ---------------------------
  * x[B,T,In] (row stride ldx), weights in the reference layout, gate order r,z,n, h0 = 0.
- * out[B,T,2H] = [forward | reverse].  gi_ws: float[B*T*6H] scratch.  gates (may be NULL when no
- * backward will follow): float[B*T*2*4*H] receives r,z,n and (W_hn h + b_hn) per (b,t,dir). */
+ * out[B,T,2H] = [forward | reverse].  gi_ws: float[s2ag_gru_fwd_ws_floats(B,T,H)] scratch (input projections
+ * + the hidden-state exchange images of the persistent tcgen05 recurrence).  gates (may be NULL when no
+ * backward will follow): float[T*2*4*H*B], layout [t][dir][gate r,z,n,(W_hn h + b_hn)][j][b]. */
+long s2ag_gru_fwd_ws_floats(int B, int T, int H);
 int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const float* w_ih_r,
                        const float* b_ih_f, const float* b_ih_r, const float* w_hh_f, const float* w_hh_r,
                        const float* b_hh_f, const float* b_hh_r, float* gi_ws, float* out, float* gates,
@@ -166,7 +168,9 @@ int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const floa
  * row of stride lddout (dir_stride = H normally; 0 when both halves share the gradient of their
  * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += ; pass all eight as NULL to
  * skip the parameter gradients (discriminator inside the generator step).
- * ws: float[B*T*6H (dgi) + B*T*6H (dgh) + 4*B*H (dh ping-pong)] */
+ * ws: float[s2ag_gru_bwd_ws_floats(B,T,H)] = B*T*6H (dgi) + B*T*6H (dgh) + 4*B*H (dh ping-pong) + the partial-product
+ * exchange buffers of the persistent tcgen05 BPTT kernel */
+long s2ag_gru_bwd_ws_floats(int B, int T, int H);
 int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride, const float* x, long ldx,
                        const float* out, const float* gates,
                        const float* w_ih_f, const float* w_ih_r, const float* w_hh_f, const float* w_hh_r,

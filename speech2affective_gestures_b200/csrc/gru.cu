@@ -11,7 +11,20 @@
 #include "gemm.cuh"
 
 using namespace s2ag;
-namespace s2ag { void launch_colsum(const float* dy, long ld, float* db, int M, int N, void* stream); }
+namespace s2ag {
+void launch_colsum(const float* dy, long ld, float* db, int M, int N, void* stream);
+#ifndef S2AG_EMU
+// umma_gru.cu: persistent weight-stationary recurrence on tcgen05
+bool gru_persist_supported(int H);
+size_t gru_persist_ws_bytes(int B, int H);
+int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const float* bhh_f, long bhh_dstride,
+                    float* out, float* gates, void* ws, int B, int T, int H, int x3, void* stream);
+size_t gru_persist_bwd_ws_bytes(int B, int H);
+int gru_persist_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
+                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, void* ws, int B, int T, int H, int x3,
+                    void* stream);
+#endif
+}  // namespace s2ag
 
 namespace {
 
@@ -77,9 +90,10 @@ __global__ void __launch_bounds__(256) gru_step_kernel(
       const float n = tanhf(gir[2 * H + j] + r * ghn);
       const float hp = has_prev ? out[((long)b * T + tprev) * 2 * H + dir * H + j] : 0.f;
       out[row * 2 * H + dir * H + j] = (1.f - z) * n + z * hp;
-      if (gates) {
-        float* gs = gates + (row * 2 + dir) * 4 * H;
-        gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = ghn;
+      if (gates) {  // saved gates: [t][dir][gate][j][b]
+        float* gs = gates + ((((long)t * 2 + dir) * 4) * H + j) * B + b;
+        const long gstride = (long)H * B;
+        gs[0] = r; gs[gstride] = z; gs[2 * gstride] = n; gs[3 * gstride] = ghn;
       }
     }
   }
@@ -101,8 +115,9 @@ __global__ void gru_bwd_gate_kernel(const float* __restrict__ dout, long lddout,
     const long row = (long)b * T + t;
     float dh = dout[row * lddout + (long)dir * dir_stride + j];
     if (step > 0) dh += carry_in[((long)dir * B + b) * H + j];
-    const float* gs = gates + (row * 2 + dir) * 4 * H;
-    const float r = gs[j], z = gs[H + j], n = gs[2 * H + j], ghn = gs[3 * H + j];
+    const float* gs = gates + ((((long)t * 2 + dir) * 4) * H + j) * B + b;  // [t][dir][gate][j][b]
+    const long gstride = (long)H * B;
+    const float r = gs[0], z = gs[gstride], n = gs[2 * gstride], ghn = gs[3 * gstride];
     const float hp = fs > 0 ? out[((long)b * T + tprev) * 2 * H + dir * H + j] : 0.f;
     const float dn = dh * (1.f - z) * (1.f - n * n);
     const float dz = dh * (hp - n) * z * (1.f - z);
@@ -116,6 +131,22 @@ __global__ void gru_bwd_gate_kernel(const float* __restrict__ dout, long lddout,
 }
 
 }  // namespace
+
+extern "C" long s2ag_gru_fwd_ws_floats(int B, int T, int H) {
+  long n = (long)B * T * 6 * H;
+#ifndef S2AG_EMU
+  n += (long)((gru_persist_ws_bytes(B, H) + 3) / 4);
+#endif
+  return n;
+}
+
+extern "C" long s2ag_gru_bwd_ws_floats(int B, int T, int H) {
+  long n = 12L * B * T * H + 4L * B * H;
+#ifndef S2AG_EMU
+  n += (long)((gru_persist_bwd_ws_bytes(B, H) + 3) / 4);
+#endif
+  return n;
+}
 
 extern "C" int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const float* w_ih_r,
                                   const float* b_ih_f, const float* b_ih_r, const float* w_hh_f, const float* w_hh_r,
@@ -132,6 +163,16 @@ extern "C" int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f,
     e.bstride = 3L * H; e.bias_bstride = (long)(b_ih_r - b_ih_f);
     launch_gemm(a, b, e, M, 3 * H, In, 2, 1, stream);
   }
+#ifndef S2AG_EMU
+  if (g_engine == 0 && gru_persist_supported(H) && gru_persist_ws_bytes(B, H) > 0) {
+    // one persistent launch (per <= 148-CTA batch chunk) for all T steps of both directions
+    int rc = gru_persist_fwd(gi_ws, w_hh_f, (long)(w_hh_r - w_hh_f), b_hh_f, (long)(b_hh_r - b_hh_f), out, gates,
+                             gi_ws + (long)M * 6 * H, B, T, H, umma::g_precision == 0 ? 1 : 0, stream);
+    if (rc != S2AG_OK) { s2ag_set_error("gru_persist_fwd failed (%d)", rc); return rc; }
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
+#endif
   dim3 grid(s2ag_cdiv(H, RJ), s2ag_cdiv(B, RB), 2);
   auto kfn = &gru_step_kernel;
   for (int s = 0; s < T; ++s)
@@ -159,7 +200,16 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
   const long total = 2L * B * H;
   int eblocks = (int)((total + 255) / 256); if (eblocks > 148 * 8) eblocks = 148 * 8;
   auto kg = &gru_bwd_gate_kernel;
-  for (int s = 0; s < T; ++s) {
+  bool persistent = false;
+#ifndef S2AG_EMU
+  if (g_engine == 0 && gru_persist_bwd_ws_bytes(B, H) > 0) {
+    int rc = gru_persist_bwd(dout, lddout, dir_stride, out, gates, w_hh_f, (long)(w_hh_r - w_hh_f), dgi, dgh,
+                             carry[0] + 4L * B * H, B, T, H, umma::g_precision == 0 ? 1 : 0, stream);
+    if (rc != S2AG_OK) { s2ag_set_error("gru_persist_bwd failed (%d)", rc); return rc; }
+    persistent = true;
+  }
+#endif
+  for (int s = 0; s < T && !persistent; ++s) {
     float* cin = carry[s & 1];
     float* cout = carry[(s + 1) & 1];
     S2AG_LAUNCH(kg, eblocks, 256, 0, stream, dout, lddout, dir_stride, out, gates, (const float*)cin, cout, dgi, dgh,

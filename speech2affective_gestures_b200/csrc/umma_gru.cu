@@ -1,0 +1,591 @@
+// Persistent, weight-stationary GRU recurrence for one bidirectional layer on tcgen05 (sm_100a).
+// Replaces the T per-step launches of gru.cu for H <= 320 (nn.GRU call sites:
+// net/multimodal_context_net_v2.py:480-481,541 (G), :281-282,333 (frozen tri-modal), :558-560,576 (D)).
+//
+// Decomposition.  grid = (S hidden slices of 16 units, batch tiles of 128 clips, 2 directions); every CTA
+// stays resident for all T steps (<= 148 CTAs, one per SM: ~214 KB of shared memory each).
+//   * W_hh stationary: the CTA's 48 rows of W_hh (gates r,z,n of its 16 hidden units) are split into bf16
+//     hi/lo once and kept in shared memory in the canonical K-major UMMA layout [k-chunk][48][16 B].
+//   * per step the CTA needs h_{t-1} of ALL hidden units of its 128 clips (the A operand,
+//     [k-chunk][128][16 B] hi/lo): the slices publish their 16 new hidden units as a ready-made bf16 hi/lo
+//     operand image in global memory (L2-resident, double-buffered by step parity); a per-(tile, direction)
+//     arrival counter (release/acquire) orders producers and consumers; the image is copied L2 -> shared
+//     memory with 16-byte ld.global.cg and consumed by tcgen05.mma (M=128, N=48, K=16; three MMAs per
+//     k-step in the fp32-grade bf16x3 mode) into a 48-column TMEM accumulator.
+//   * epilogue (thread = clip, 8 hidden units each): tcgen05.ld, gate math in fp32 with the step's gi
+//     prefetched before the wait, h kept in registers across steps, writes out[b,t,dir*H+j], the saved
+//     gates (layout [t][dir][gate][j][b]: coalesced along b) and the next operand image.
+// Gate math follows PyTorch: r,z = sigmoid, n = tanh(gi_n + r*(W_hn h + b_hn)),
+// h' = (1-z)*n + z*h, h0 = 0.
+#include "s2ag.h"
+#include "gemm_umma.cuh"
+
+namespace s2ag {
+namespace grup {
+
+using namespace s2ag::umma;
+
+constexpr int PBM = 128, HS = 16, NC = 48, PTHREADS = 256, HDR = 128;
+
+struct Params {
+  const float* gi;          // [B*T][2][3H]  (x W_ih^T + b_ih)
+  const float* whh;         // direction 0; direction 1 at + whh_dstride
+  long whh_dstride;
+  const float* bhh;
+  long bhh_dstride;
+  float* out;               // [B][T][2H]
+  float* gates;             // [T][2][4][H][B] or nullptr
+  unsigned char* xchg;      // operand images: [group][parity][hi|lo][Kpad/8][128][16 B]
+  unsigned int* cnt;        // one arrival counter per group, 32 words apart
+  int B, T, H, Kpad, S, nbt, bt0, x3;  // nbt: batch tiles of the whole batch; bt0: first tile of this launch
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * p], v[2 * p + 1]);
+    h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * p] - __low2float(hh), v[2 * p + 1] - __high2float(hh));
+    l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(PTHREADS, 1) gru_persist_fwd_kernel(Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad;
+  const int nchunk = Kpad >> 3;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mma_bar = sbase;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8);
+  unsigned char* w_hi = smem + HDR;                   // [nchunk][48][16]
+  unsigned char* w_lo = w_hi + nchunk * NC * 16;
+  unsigned char* a_hi = w_lo + nchunk * NC * 16;      // [nchunk][128][16]
+  const int a_half = nchunk * PBM * 16;
+  const int group = dir * p.nbt + bt;
+  const unsigned* cnt = p.cnt + group * 32;
+  unsigned char* img0 = p.xchg + (size_t)group * 2 * (2 * (size_t)a_half);
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(sbase + 8, 64);
+
+  // ---- stationary W_hh slice: rows n = g*16 + jj  <->  W_hh[g*H + j0 + jj][k]
+  const float* whh = p.whh + dir * p.whh_dstride;
+  const int j0 = slice * HS;
+  for (int idx = tid; idx < nchunk * NC; idx += PTHREADS) {
+    const int n = idx % NC, kc = idx / NC;
+    const int g = n / HS, j = j0 + n % HS;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * 8 + i;
+      v[i] = (j < H && k < H) ? __ldg(whh + ((long)g * H + j) * H + k) : 0.f;
+    }
+    uint4 hi, lo;
+    pack8(v, hi, lo);
+    *reinterpret_cast<uint4*>(w_hi + (kc * NC + n) * 16) = hi;
+    *reinterpret_cast<uint4*>(w_lo + (kc * NC + n) * 16) = lo;
+  }
+
+  // ---- per-thread epilogue assignment: clip row, 8 hidden units
+  const int row = (warp & 3) * 32 + lane;
+  const int b = bt * PBM + row;
+  const int u0 = (warp >> 2) * 8;          // unit offset inside the slice
+  const int jb = j0 + u0;                  // first hidden unit of this thread
+  const bool b_ok = b < B;
+  // 16-byte accesses to gi / out rows: all 8 units valid and every row segment 16-byte aligned
+  const bool vec_ok = (H & 3) == 0 && jb + 8 <= H && ((reinterpret_cast<uintptr_t>(p.gi) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+  const float* bhh = p.bhh + dir * p.bhh_dstride;
+  float br[8], bz[8], bn[8], h_own[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = jb + i < H;
+    br[i] = ok ? __ldg(bhh + jb + i) : 0.f;
+    bz[i] = ok ? __ldg(bhh + H + jb + i) : 0.f;
+    bn[i] = ok ? __ldg(bhh + 2 * H + jb + i) : 0.f;
+    h_own[i] = 0.f;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc(NC);
+  const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    // gi of this step: independent of the recurrence, issue the loads first
+    float gr[8], gz[8], gn[8];
+    {
+      const float* g = p.gi + ((long)(b_ok ? b : 0) * T + t) * 6 * H + (long)dir * 3 * H + jb;
+      if (vec_ok) {
+        if (b_ok) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(g)), r1 = __ldg(reinterpret_cast<const float4*>(g) + 1);
+          const float4 z0 = __ldg(reinterpret_cast<const float4*>(g + H)), z1 = __ldg(reinterpret_cast<const float4*>(g + H) + 1);
+          const float4 n0 = __ldg(reinterpret_cast<const float4*>(g + 2 * H)), n1 = __ldg(reinterpret_cast<const float4*>(g + 2 * H) + 1);
+          gr[0] = r0.x; gr[1] = r0.y; gr[2] = r0.z; gr[3] = r0.w; gr[4] = r1.x; gr[5] = r1.y; gr[6] = r1.z; gr[7] = r1.w;
+          gz[0] = z0.x; gz[1] = z0.y; gz[2] = z0.z; gz[3] = z0.w; gz[4] = z1.x; gz[5] = z1.y; gz[6] = z1.z; gz[7] = z1.w;
+          gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[i] = gz[i] = gn[i] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = b_ok && jb + i < H;
+          gr[i] = ok ? __ldg(g + i) : 0.f;
+          gz[i] = ok ? __ldg(g + H + i) : 0.f;
+          gn[i] = ok ? __ldg(g + 2 * H + i) : 0.f;
+        }
+      }
+    }
+    float ar[8], az[8], an[8];
+    if (s > 0) {
+      // all S slices of this (tile, direction) have published h_{s-1}
+      if (tid == 0) {
+        const unsigned target = (unsigned)p.S * (unsigned)s;
+        unsigned spins = 0;
+        while (ld_acquire_u32(cnt) < target) {
+          if (++spins > (1u << 26)) __trap();
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      // operand image (parity (s-1)&1): L2 -> shared memory, 16-byte cp.async.cg (L1 bypassed, no register staging)
+      {
+        const unsigned char* src = img0 + (size_t)((s - 1) & 1) * 2 * a_half;
+        const uint32_t dst = smem_u32(a_hi);
+        const int nbytes = (p.x3 ? 2 : 1) * a_half;
+        for (int off = tid * 16; off < nbytes; off += PTHREADS * 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
+        const uint32_t a_lbo = PBM * 16, w_lbo = NC * 16;
+        for (int kk = 0; kk < (Kpad >> 4); ++kk) {
+          const uint32_t ah = sa + kk * 2 * a_lbo, al = ah + a_half;
+          const uint32_t wh = sw + kk * 2 * w_lbo, wl = wh + nchunk * NC * 16;
+          const uint64_t dah = make_desc(ah, a_lbo, 128), dwh = make_desc(wh, w_lbo, 128);
+          uint32_t acc = kk > 0 ? 1u : 0u;
+          if (p.x3) {
+            mma_bf16(tmem_base, make_desc(al, a_lbo, 128), dwh, idesc, acc);
+            mma_bf16(tmem_base, dah, make_desc(wl, w_lbo, 128), idesc, 1u);
+            acc = 1u;
+          }
+          mma_bf16(tmem_base, dah, dwh, idesc, acc);
+        }
+        mma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, (uint32_t)((s - 1) & 1));
+      tc_fence_after();
+      tmem_ld8(t_lane + (uint32_t)(0 * HS + u0), ar);
+      tmem_ld8(t_lane + (uint32_t)(1 * HS + u0), az);
+      tmem_ld8(t_lane + (uint32_t)(2 * HS + u0), an);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ar[i] = az[i] = an[i] = 0.f;
+    }
+    // gate math + stores
+    float* orow = p.out + ((long)(b_ok ? b : 0) * T + t) * 2 * H + (long)dir * H + jb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = b_ok && jb + i < H;
+      const float ghn = an[i] + bn[i];
+      const float r = s2ag_sigmoid(gr[i] + ar[i] + br[i]);
+      const float z = s2ag_sigmoid(gz[i] + az[i] + bz[i]);
+      const float n = tanhf(gn[i] + r * ghn);
+      const float h = (1.f - z) * n + z * h_own[i];
+      h_own[i] = ok ? h : 0.f;
+      if (ok) {
+        if (!vec_ok) orow[i] = h;
+        if (p.gates) {
+          float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + (jb + i)) * B + b;
+          const long gstride = (long)H * B;
+          gs[0] = r; gs[gstride] = z; gs[2 * gstride] = n; gs[3 * gstride] = ghn;
+        }
+      }
+    }
+    if (vec_ok && b_ok) {
+      reinterpret_cast<float4*>(orow)[0] = make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
+      reinterpret_cast<float4*>(orow)[1] = make_float4(h_own[4], h_own[5], h_own[6], h_own[7]);
+    }
+    if (s + 1 < T) {
+      // publish the operand image of h_s (parity s&1): chunk (jb/8), row `row`
+      uint4 hi, lo;
+      pack8(h_own, hi, lo);
+      unsigned char* img = img0 + (size_t)(s & 1) * 2 * a_half;
+      const int off = ((jb >> 3) * PBM + row) * 16;
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      if (p.x3) *reinterpret_cast<uint4*>(img + a_half + off) = lo;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (s + 1 < T && tid == 0) {
+      __threadfence();
+      atomicAdd(const_cast<unsigned*>(cnt), 1u);
+    }
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BPTT.  Same ownership (CTA = 16 hidden units x 128 clips x direction, resident for all T steps).  Per step
+// (forward order reversed) the CTA computes the gate gradients of its units locally,
+//   dh = dout + carry;  dn = dh(1-z)(1-n^2);  dz = dh(h_prev - n)z(1-z);  dr = dn*ghn*r(1-r),
+// writes dgi = (dr,dz,dn) and dgh = (dr,dz,dn*r) for the time-batched weight-gradient GEMMs, and contributes
+//   partial[b, k] = sum_{c in its 48 gate rows} dgh[b,c] * W_hh[c, k]          (all k: M=128, N=Kpad, K=48)
+// on tcgen05 (A = its own dgh, split hi/lo from registers; B = its 48 rows of W_hh, stationary, stored as
+// [k-chunk of c][n = k][16 B]).  The partials ([slice][k][b], coalesced along b) are exchanged through L2; after
+// the per-(tile, direction) arrival counter each CTA sums the 16 columns it owns over all slices:
+//   carry[b, j] = dh*z + sum_slices partial_s[b, j].
+struct BwdParams {
+  const float* dout; long lddout; int dir_stride;
+  const float* out;         // [B][T][2H] forward output (h_prev)
+  const float* gates;       // [T][2][4][H][B]
+  const float* whh; long whh_dstride;
+  float* dgi;               // [B*T][2][3H]
+  float* dgh;               // [B*T][2][3H]
+  float* part;              // [group][parity][S][Kpad][128]
+  unsigned int* cnt;
+  int B, T, H, Kpad, S, nbt, bt0, x3;
+};
+
+__global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad, S = p.S;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mma_bar = sbase;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8);
+  // B operand: [6 k-chunks][Kpad rows n][16 B] hi, then lo ; A operand: [6 k-chunks][128][16 B] hi, then lo
+  unsigned char* w_hi = smem + HDR;
+  const int w_half = 6 * Kpad * 16;
+  unsigned char* w_lo = w_hi + w_half;
+  unsigned char* a_hi = w_lo + w_half;
+  const int a_half = 6 * PBM * 16;
+  unsigned char* a_lo = a_hi + a_half;
+  const int group = dir * p.nbt + bt;
+  const unsigned* cnt = p.cnt + group * 32;
+  const size_t part_slice = (size_t)Kpad * PBM;            // floats of one slice's partial
+  float* part0 = p.part + (size_t)group * 2 * S * part_slice;
+  const uint32_t ncols = Kpad <= 32 ? 32u : Kpad <= 64 ? 64u : Kpad <= 128 ? 128u : Kpad <= 256 ? 256u : 512u;
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(sbase + 8, ncols);
+
+  // ---- stationary W_hh rows of this slice, transposed for the B operand: element (n = k_out, kk = c_local)
+  const float* whh = p.whh + dir * p.whh_dstride;
+  const int j0 = slice * HS;
+  for (int idx = tid; idx < 6 * Kpad; idx += PTHREADS) {
+    const int n = idx % Kpad, kc = idx / Kpad;       // kc: chunk of 8 local gate rows
+    const int g = kc >> 1, jj0 = (kc & 1) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + jj0 + i;
+      v[i] = (j < H && n < H) ? __ldg(whh + ((long)g * H + j) * H + n) : 0.f;
+    }
+    uint4 hi, lo;
+    pack8(v, hi, lo);
+    *reinterpret_cast<uint4*>(w_hi + (kc * Kpad + n) * 16) = hi;
+    *reinterpret_cast<uint4*>(w_lo + (kc * Kpad + n) * 16) = lo;
+  }
+
+  const int row = (warp & 3) * 32 + lane;
+  const int b = bt * PBM + row;
+  const int wg = warp >> 2;
+  const int u0 = wg * 8, jb = j0 + u0;
+  const bool b_ok = b < B;
+  const bool vec_ok = (H & 3) == 0 && jb + 8 <= H && (p.lddout & 3) == 0 && ((p.dir_stride & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.dout) | reinterpret_cast<uintptr_t>(p.out) |
+                        reinterpret_cast<uintptr_t>(p.dgi) | reinterpret_cast<uintptr_t>(p.dgh)) & 15) == 0;
+  float carry[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) carry[i] = 0.f;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  // N split: one MMA covers at most 256 accumulator columns
+  const int n1 = Kpad <= 256 ? Kpad : 160, n2 = Kpad - n1;
+
+  for (int step = 0; step < T; ++step) {
+    const int fs = T - 1 - step;                         // forward step index being differentiated
+    const int t = dir == 0 ? fs : T - 1 - fs;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    const long rowi = (long)(b_ok ? b : 0) * T + t;
+    float dh[8], hp[8], r[8], z[8], n[8], ghn[8];
+    {
+      const float* dp = p.dout + rowi * p.lddout + (long)dir * p.dir_stride + jb;
+      const float* hq = p.out + ((long)(b_ok ? b : 0) * T + (fs > 0 ? tprev : t)) * 2 * H + (long)dir * H + jb;
+      if (vec_ok && b_ok) {
+        const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+        dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
+        if (fs > 0) {
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(hq)), h1 = __ldg(reinterpret_cast<const float4*>(hq) + 1);
+          hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w; hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hp[i] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = b_ok && jb + i < H;
+          dh[i] = ok ? __ldg(dp + i) : 0.f;
+          hp[i] = (ok && fs > 0) ? __ldg(hq + i) : 0.f;
+        }
+      }
+      const float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + jb) * B + (b_ok ? b : 0);
+      const long gstride = (long)H * B;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = b_ok && jb + i < H;
+        r[i] = ok ? __ldg(gs + (long)i * B) : 0.f;
+        z[i] = ok ? __ldg(gs + gstride + (long)i * B) : 0.f;
+        n[i] = ok ? __ldg(gs + 2 * gstride + (long)i * B) : 0.f;
+        ghn[i] = ok ? __ldg(gs + 3 * gstride + (long)i * B) : 0.f;
+      }
+    }
+    float dr[8], dz[8], dn[8], dnr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dh[i] += carry[i];
+      dn[i] = dh[i] * (1.f - z[i]) * (1.f - n[i] * n[i]);
+      dz[i] = dh[i] * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
+      dr[i] = dn[i] * ghn[i] * r[i] * (1.f - r[i]);
+      dnr[i] = dn[i] * r[i];
+      carry[i] = dh[i] * z[i];
+    }
+    if (b_ok) {  // dgi / dgh rows for the time-batched weight-gradient GEMMs
+      float* a = p.dgi + (rowi * 2 + dir) * 3 * H + jb;
+      float* c = p.dgh + (rowi * 2 + dir) * 3 * H + jb;
+      if (vec_ok) {
+        float4* a4; float4* c4;
+        a4 = reinterpret_cast<float4*>(a); c4 = reinterpret_cast<float4*>(c);
+        a4[0] = make_float4(dr[0], dr[1], dr[2], dr[3]); a4[1] = make_float4(dr[4], dr[5], dr[6], dr[7]);
+        c4[0] = a4[0]; c4[1] = a4[1];
+        a4 = reinterpret_cast<float4*>(a + H); c4 = reinterpret_cast<float4*>(c + H);
+        a4[0] = make_float4(dz[0], dz[1], dz[2], dz[3]); a4[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
+        c4[0] = a4[0]; c4[1] = a4[1];
+        a4 = reinterpret_cast<float4*>(a + 2 * H); c4 = reinterpret_cast<float4*>(c + 2 * H);
+        a4[0] = make_float4(dn[0], dn[1], dn[2], dn[3]); a4[1] = make_float4(dn[4], dn[5], dn[6], dn[7]);
+        c4[0] = make_float4(dnr[0], dnr[1], dnr[2], dnr[3]); c4[1] = make_float4(dnr[4], dnr[5], dnr[6], dnr[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (jb + i < H) {
+            a[i] = dr[i]; a[H + i] = dz[i]; a[2 * H + i] = dn[i];
+            c[i] = dr[i]; c[H + i] = dz[i]; c[2 * H + i] = dnr[i];
+          }
+        }
+      }
+    }
+    if (fs > 0) {
+      // A operand = this CTA's dgh tile [128 x 48]: local gate row c = g*16 + u0 + i  ->  chunk g*2 + wg
+      {
+        uint4 hi, lo;
+        pack8(dr, hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + ((0 * 2 + wg) * PBM + row) * 16) = hi;
+        *reinterpret_cast<uint4*>(a_lo + ((0 * 2 + wg) * PBM + row) * 16) = lo;
+        pack8(dz, hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + ((1 * 2 + wg) * PBM + row) * 16) = hi;
+        *reinterpret_cast<uint4*>(a_lo + ((1 * 2 + wg) * PBM + row) * 16) = lo;
+        pack8(dnr, hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + ((2 * 2 + wg) * PBM + row) * 16) = hi;
+        *reinterpret_cast<uint4*>(a_lo + ((2 * 2 + wg) * PBM + row) * 16) = lo;
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
+        const uint32_t a_lbo = PBM * 16, w_lbo = (uint32_t)Kpad * 16;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nn = half == 0 ? n1 : n2;
+          if (nn == 0) continue;
+          const uint32_t idesc = make_idesc(nn);
+          const uint32_t d_tmem = tmem_base + (half == 0 ? 0u : (uint32_t)n1);
+          const uint32_t w_off = half == 0 ? 0u : (uint32_t)n1 * 16u;
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const uint32_t ah = sa + kk * 2 * a_lbo, al = ah + a_half;
+            const uint32_t wh = sw + kk * 2 * w_lbo + w_off, wl = wh + w_half;
+            const uint64_t dah = make_desc(ah, a_lbo, 128), dwh = make_desc(wh, w_lbo, 128);
+            uint32_t acc = kk > 0 ? 1u : 0u;
+            if (p.x3) {
+              mma_bf16(d_tmem, make_desc(al, a_lbo, 128), dwh, idesc, acc);
+              mma_bf16(d_tmem, dah, make_desc(wl, w_lbo, 128), idesc, 1u);
+              acc = 1u;
+            }
+            mma_bf16(d_tmem, dah, dwh, idesc, acc);
+          }
+        }
+        mma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, (uint32_t)(step & 1));
+      tc_fence_after();
+      // accumulator -> partial[parity][slice][k][b]; warpgroup wg takes the k-columns [wg*Kpad/2, +Kpad/2)
+      float* mypart = part0 + ((size_t)(step & 1) * S + slice) * part_slice;
+      const int kh = Kpad >> 1;
+      for (int c0 = wg * kh; c0 < (wg + 1) * kh; c0 += 8) {
+        float v[8];
+        tmem_ld8(t_lane + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mypart[(size_t)(c0 + i) * PBM + row] = v[i];
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(const_cast<unsigned*>(cnt), 1u);
+        const unsigned target = (unsigned)S * (unsigned)(step + 1);
+        unsigned spins = 0;
+        while (ld_acquire_u32(cnt) < target) {
+          if (++spins > (1u << 26)) __trap();
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      // carry[b, j] += sum over slices of their partial columns j (this thread: 8 columns, its clip)
+      const float* pp = part0 + (size_t)(step & 1) * S * part_slice + (size_t)jb * PBM + row;
+      for (int sl = 0; sl < S; ++sl) {
+        const float* q = pp + (size_t)sl * part_slice;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) carry[i] += __ldcg(q + (size_t)i * PBM);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+static inline int kpad_of(int H) { return ((H + HS - 1) / HS) * HS; }
+static inline size_t img_bytes(int H) { return 2 * (size_t)(kpad_of(H) / 8) * PBM * 16; }  // hi + lo
+static inline size_t persist_smem_bytes(int H) { return HDR + (size_t)kpad_of(H) / 8 * (2 * NC + 2 * PBM) * 16; }
+
+}  // namespace grup
+
+// A launch keeps every CTA resident: at most 148 CTAs -> batch chunks of `rows_per_launch` clips.
+bool gru_persist_supported(int H) { return H >= 16 && grup::persist_smem_bytes(H) <= 227 * 1024; }
+static int gru_persist_tiles_per_launch(int H) {
+  const int S = grup::kpad_of(H) / grup::HS;
+  int tiles = 148 / (2 * S);
+  return tiles < 1 ? 0 : tiles;
+}
+// bytes of exchange workspace (operand images + counters) for a batch of B clips
+size_t gru_persist_ws_bytes(int B, int H) {
+  if (!gru_persist_supported(H) || gru_persist_tiles_per_launch(H) == 0) return 0;
+  const int nbt = (B + grup::PBM - 1) / grup::PBM;
+  return (size_t)2 * nbt * 2 * grup::img_bytes(H) + (size_t)2 * nbt * 32 * sizeof(unsigned) + 256;
+}
+
+int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const float* bhh_f, long bhh_dstride,
+                    float* out, float* gates, void* ws, int B, int T, int H, int x3, void* stream) {
+  using namespace grup;
+  const int S = kpad_of(H) / HS;
+  const int tiles_max = gru_persist_tiles_per_launch(H);
+  if (tiles_max == 0 || !gru_persist_supported(H)) return S2AG_ERR_UNSUPPORTED;
+  auto kfn = &gru_persist_fwd_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int nbt_all = (B + PBM - 1) / PBM;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  base += (256 - (reinterpret_cast<uintptr_t>(base) & 255)) & 255;
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(base);
+  unsigned char* xchg = base + (((size_t)2 * nbt_all * 32 * sizeof(unsigned) + 255) & ~(size_t)255);
+  if (cudaMemsetAsync(cnt, 0, (size_t)2 * nbt_all * 32 * sizeof(unsigned), (cudaStream_t)stream) != cudaSuccess)
+    return S2AG_ERR_LAUNCH;
+  for (int t0 = 0; t0 < nbt_all; t0 += tiles_max) {  // every launch keeps all of its CTAs resident
+    const int nbt = nbt_all - t0 < tiles_max ? nbt_all - t0 : tiles_max;
+    Params p;
+    p.gi = gi; p.whh = whh_f; p.whh_dstride = whh_dstride; p.bhh = bhh_f; p.bhh_dstride = bhh_dstride;
+    p.out = out; p.gates = gates; p.xchg = xchg; p.cnt = cnt;
+    p.B = B; p.T = T; p.H = H; p.Kpad = kpad_of(H); p.S = S; p.nbt = nbt_all; p.bt0 = t0; p.x3 = x3;
+    S2AG_LAUNCH(kfn, dim3(S, nbt, 2), PTHREADS, persist_smem_bytes(H), stream, p);
+  }
+  return S2AG_OK;
+}
+
+
+static size_t bwd_smem_bytes(int H) { return grup::HDR + (size_t)2 * 6 * 16 * (grup::kpad_of(H) + grup::PBM); }
+size_t gru_persist_bwd_ws_bytes(int B, int H) {
+  if (!gru_persist_supported(H) || gru_persist_tiles_per_launch(H) == 0) return 0;
+  if (grup::kpad_of(H) > 512) return 0;
+  const int nbt = (B + grup::PBM - 1) / grup::PBM;
+  const int S = grup::kpad_of(H) / grup::HS;
+  return (size_t)2 * nbt * 2 * S * grup::kpad_of(H) * grup::PBM * sizeof(float) + (size_t)2 * nbt * 32 * sizeof(unsigned) + 512;
+}
+
+int gru_persist_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
+                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, void* ws, int B, int T, int H, int x3,
+                    void* stream) {
+  using namespace grup;
+  const int S = kpad_of(H) / HS;
+  const int tiles_max = gru_persist_tiles_per_launch(H);
+  if (tiles_max == 0 || gru_persist_bwd_ws_bytes(B, H) == 0) return S2AG_ERR_UNSUPPORTED;
+  auto kfn = &gru_persist_bwd_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int nbt_all = (B + PBM - 1) / PBM;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  base += (256 - (reinterpret_cast<uintptr_t>(base) & 255)) & 255;
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(base);
+  float* part = reinterpret_cast<float*>(base + (((size_t)2 * nbt_all * 32 * sizeof(unsigned) + 255) & ~(size_t)255));
+  if (cudaMemsetAsync(cnt, 0, (size_t)2 * nbt_all * 32 * sizeof(unsigned), (cudaStream_t)stream) != cudaSuccess)
+    return S2AG_ERR_LAUNCH;
+  for (int t0 = 0; t0 < nbt_all; t0 += tiles_max) {
+    const int nbt = nbt_all - t0 < tiles_max ? nbt_all - t0 : tiles_max;
+    BwdParams p;
+    p.dout = dout; p.lddout = lddout; p.dir_stride = dir_stride; p.out = out; p.gates = gates;
+    p.whh = whh_f; p.whh_dstride = whh_dstride; p.dgi = dgi; p.dgh = dgh; p.part = part; p.cnt = cnt;
+    p.B = B; p.T = T; p.H = H; p.Kpad = kpad_of(H); p.S = S; p.nbt = nbt_all; p.bt0 = t0; p.x3 = x3;
+    S2AG_LAUNCH(kfn, dim3(S, nbt, 2), PTHREADS, bwd_smem_bytes(H), stream, p);
+  }
+  return S2AG_OK;
+}
+
+}  // namespace s2ag

@@ -514,7 +514,7 @@ class BiGruFn(torch.autograd.Function):
         x2, ldx = _rows(x, In0)
         st = _stream(x)
         need_bwd = any(ctx.needs_input_grad)
-        gi_ws = _empty((B * T * 6 * H,), x)
+        gi_ws = _empty((_C.lib().s2ag_gru_fwd_ws_floats(B, T, H),), x)
         layers = []
         cur, ldcur, In = x2, ldx, In0
         for l in range(nlayers):
@@ -549,7 +549,7 @@ class BiGruFn(torch.autograd.Function):
         B, T, In0, H, nlayers, sum_halves, slices, npieces = ctx.cfg
         st = _stream(dy)
         M = B * T
-        ws = _empty((M * 12 * H + 4 * B * H,), dy)
+        ws = _empty((_C.lib().s2ag_gru_bwd_ws_floats(B, T, H),), dy)
         if sum_halves:
             d, ldd = _rows(dy, H)
             dstride = 0
