@@ -14,6 +14,17 @@ namespace s2ag {
 constexpr int GBM = 64, GBN = 64, GBK = 16, GTHREADS = 256;
 
 // ---------------------------------------------------------------- loaders
+// Every loader offers two interfaces:
+//   float operator()(batch, row, k)                      -- random access (SIMT engine, tests)
+//   Cur cursor(batch, row, k0); load8(cur, kend, v[8]); advance(cur)
+//        -- streaming access for the tcgen05 engine: a cursor pins one operand row and walks k in steps of 32
+//           (advance), load8 fetches the 8 consecutive k at the cursor (zeros beyond kend).  All row-dependent
+//           index arithmetic (pixel decomposition, base pointers) is done once per tile in cursor(); mixed-radix
+//           k indices are carried incrementally instead of being re-divided per element.
+constexpr int LD_STEP = 32;  // k advance per cursor step (= the tcgen05 engine's k-block)
+
+__device__ __forceinline__ bool s2ag_aligned16(const void* q) { return (reinterpret_cast<unsigned long long>(q) & 15ull) == 0; }
+
 // element(batch,row,k) = p[batch*bstride + row*ld_row + k*ld_k]
 template <bool KCONTIG>
 struct LdPlain {
@@ -22,18 +33,25 @@ struct LdPlain {
   __device__ __forceinline__ float operator()(int b, int row, int k) const {
     return __ldg(p + b * bstride + (long)row * ld_row + (long)k * ld_k);
   }
-  // 4 consecutive k (zero beyond kend); one 16-byte load when k is the contiguous axis and the address is aligned
-  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
-    const float* q = p + b * bstride + (long)row * ld_row + (long)k * ld_k;
-    if (KCONTIG && k + 4 <= kend && ld_k == 1 && (reinterpret_cast<unsigned long long>(q) & 15ull) == 0)
-      return __ldg(reinterpret_cast<const float4*>(q));
-    float4 r;
-    r.x = k < kend ? __ldg(q) : 0.f;
-    r.y = k + 1 < kend ? __ldg(q + ld_k) : 0.f;
-    r.z = k + 2 < kend ? __ldg(q + 2 * ld_k) : 0.f;
-    r.w = k + 3 < kend ? __ldg(q + 3 * ld_k) : 0.f;
-    return r;
+  struct Cur { const float* q; int k; };
+  __device__ __forceinline__ Cur cursor(int b, int row, int k) const {
+    return Cur{p + b * bstride + (long)row * ld_row + (long)k * ld_k, k};
   }
+  __device__ __forceinline__ void load8(const Cur& c, int kend, float (&v)[8]) const {
+    if (c.k + 8 <= kend) {
+      if (KCONTIG && ld_k == 1 && s2ag_aligned16(c.q)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(c.q)), b = __ldg(reinterpret_cast<const float4*>(c.q) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(c.q + i * ld_k);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (c.k + i < kend) ? __ldg(c.q + i * ld_k) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void advance(Cur& c) const { c.q += LD_STEP * ld_k; c.k += LD_STEP; }
 };
 
 // Implicit im2col over a channels-last activation x[N][H][W][C] (Conv1d: W == 1).
@@ -44,54 +62,120 @@ constexpr int ORDER_CKK = 0, ORDER_KKC = 1;
 template <int ORDER>
 struct LdConv {
   static constexpr bool kContig = true;
+  static constexpr int kOrder = ORDER;
   const float* x; int H, W, C;       // source geometry
   int Ho, Wo;                        // row space geometry
   int KH, KW, sh, sw, dh, dw, sgn, off_h, off_w;
   long ldpix;                        // floats between consecutive pixels of x (>= C; lets x be a column slice)
-  __device__ __forceinline__ float operator()(int, int row, int k) const {
-    int wo = row % Wo; int t = row / Wo; int ho = t % Ho; int n = t / Ho;
-    int c, kh, kw;
+  __device__ __forceinline__ void split_k(int k, int& c, int& kh, int& kw) const {
     if (ORDER == ORDER_CKK) { kw = k % KW; int t2 = k / KW; kh = t2 % KH; c = t2 / KH; }
-    else { c = k % C; int t2 = k / C; kw = t2 % KW; kh = t2 / KW; }
+    else { c = k % C; int t2 = k / C; if (KW == 1) { kw = 0; kh = t2; } else { kw = t2 % KW; kh = t2 / KW; } }
+  }
+  __device__ __forceinline__ void split_row(int row, int& n, int& ho, int& wo) const {
+    if (Wo == 1) { wo = 0; ho = row % Ho; n = row / Ho; } else { wo = row % Wo; int t = row / Wo; ho = t % Ho; n = t / Ho; }
+  }
+  __device__ __forceinline__ float operator()(int, int row, int k) const {
+    int n, ho, wo, c, kh, kw;
+    split_row(row, n, ho, wo);
+    split_k(k, c, kh, kw);
     int hi = ho * sh + sgn * kh * dh + off_h;
     int wi = wo * sw + sgn * kw * dw + off_w;
     if (hi < 0 || hi >= H || wi < 0 || wi >= W) return 0.f;
     return __ldg(x + ((long)(n * H + hi) * W + wi) * ldpix + c);
   }
-  // 4 consecutive k: with the (kh, kw, c) order and C % 4 == 0 they are 4 channels of ONE pixel
-  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
-    if (ORDER == ORDER_KKC && (C & 3) == 0 && k + 4 <= kend) {
-      int wo = row % Wo; int t = row / Wo; int ho = t % Ho; int n = t / Ho;
-      int c = k % C; int t2 = k / C; int kw = t2 % KW; int kh = t2 / KW;
-      int hi = ho * sh + sgn * kh * dh + off_h;
-      int wi = wo * sw + sgn * kw * dw + off_w;
-      if (hi < 0 || hi >= H || wi < 0 || wi >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* q = x + ((long)(n * H + hi) * W + wi) * ldpix + c;
-      if ((reinterpret_cast<unsigned long long>(q) & 15ull) == 0) return __ldg(reinterpret_cast<const float4*>(q));
-      return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+  struct Cur { const float* xn; int hi0, wi0, k, c, kh, kw; };
+  __device__ __forceinline__ Cur cursor(int, int row, int k) const {
+    int n, ho, wo;
+    split_row(row, n, ho, wo);
+    Cur cu;
+    cu.xn = x + (long)n * H * W * ldpix;
+    cu.hi0 = ho * sh + off_h; cu.wi0 = wo * sw + off_w; cu.k = k;
+    split_k(k, cu.c, cu.kh, cu.kw);
+    return cu;
+  }
+  __device__ __forceinline__ const float* pix(const Cur& cu, int kh, int kw) const {  // nullptr outside the image
+    const int hi = cu.hi0 + sgn * kh * dh, wi = cu.wi0 + sgn * kw * dw;
+    if (hi < 0 || hi >= H || wi < 0 || wi >= W) return nullptr;
+    return cu.xn + ((long)hi * W + wi) * ldpix;
+  }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+    int c = cu.c, kh = cu.kh, kw = cu.kw;
+    if (ORDER == ORDER_KKC && (C & 3) == 0 && cu.k + 8 <= kend) {
+      // two groups of 4 channels, each inside one pixel (k % 4 == 0 and C % 4 == 0)
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float* q = pix(cu, kh, kw);
+        if (q) {
+          q += c;
+          if (s2ag_aligned16(q)) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+            v[4 * g] = a.x; v[4 * g + 1] = a.y; v[4 * g + 2] = a.z; v[4 * g + 3] = a.w;
+          } else {
+            v[4 * g] = __ldg(q); v[4 * g + 1] = __ldg(q + 1); v[4 * g + 2] = __ldg(q + 2); v[4 * g + 3] = __ldg(q + 3);
+          }
+        } else {
+          v[4 * g] = v[4 * g + 1] = v[4 * g + 2] = v[4 * g + 3] = 0.f;
+        }
+        c += 4;
+        if (c >= C) { c -= C; if (++kw == KW) { kw = 0; ++kh; } }
+      }
+      return;
     }
-    float4 r;
-    r.x = k < kend ? (*this)(b, row, k) : 0.f;
-    r.y = k + 1 < kend ? (*this)(b, row, k + 1) : 0.f;
-    r.z = k + 2 < kend ? (*this)(b, row, k + 2) : 0.f;
-    r.w = k + 3 < kend ? (*this)(b, row, k + 3) : 0.f;
-    return r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float val = 0.f;
+      if (cu.k + i < kend) {
+        const float* q = pix(cu, kh, kw);
+        if (q) val = __ldg(q + c);
+      }
+      v[i] = val;
+      if (ORDER == ORDER_CKK) { if (++kw == KW) { kw = 0; if (++kh == KH) { kh = 0; ++c; } } }
+      else { if (++c == C) { c = 0; if (++kw == KW) { kw = 0; ++kh; } } }
+    }
+  }
+  __device__ __forceinline__ void advance(Cur& cu) const {
+    cu.k += LD_STEP;
+    if (ORDER == ORDER_KKC) {
+      cu.c += LD_STEP;
+      while (cu.c >= C) { cu.c -= C; if (++cu.kw == KW) { cu.kw = 0; ++cu.kh; } }
+    } else {
+      split_k(cu.k, cu.c, cu.kh, cu.kw);
+    }
   }
 };
 
-// Transposed view of another loader (swap the roles of row and k).
+// Transposed view of an implicit-im2col loader (swap the roles of row and k): element(row, k) = l(k, row).
+// row = the conv's k index (c, kh, kw), fixed per cursor; k walks the pixels (n, ho, wo).
 template <class L>
 struct LdT {
   static constexpr bool kContig = !L::kContig;
   L l;
   __device__ __forceinline__ float operator()(int b, int row, int k) const { return l(b, k, row); }
-  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
-    float4 r;
-    r.x = k < kend ? l(b, k, row) : 0.f;
-    r.y = k + 1 < kend ? l(b, k + 1, row) : 0.f;
-    r.z = k + 2 < kend ? l(b, k + 2, row) : 0.f;
-    r.w = k + 3 < kend ? l(b, k + 3, row) : 0.f;
-    return r;
+  struct Cur { int c, kh, kw, p, n, ho, wo; };
+  __device__ __forceinline__ Cur cursor(int, int row, int k) const {
+    Cur cu;
+    l.split_k(row, cu.c, cu.kh, cu.kw);
+    cu.p = k;
+    l.split_row(k, cu.n, cu.ho, cu.wo);
+    return cu;
+  }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+    int n = cu.n, ho = cu.ho, wo = cu.wo;
+    const int dhh = l.sgn * cu.kh * l.dh + l.off_h, dww = l.sgn * cu.kw * l.dw + l.off_w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float val = 0.f;
+      if (cu.p + i < kend) {
+        const int hi = ho * l.sh + dhh, wi = wo * l.sw + dww;
+        if (hi >= 0 && hi < l.H && wi >= 0 && wi < l.W) val = __ldg(l.x + ((long)(n * l.H + hi) * l.W + wi) * l.ldpix + cu.c);
+      }
+      v[i] = val;
+      if (++wo == l.Wo) { wo = 0; if (++ho == l.Ho) { ho = 0; ++n; } }
+    }
+  }
+  __device__ __forceinline__ void advance(Cur& cu) const {
+    cu.p += LD_STEP;
+    l.split_row(cu.p, cu.n, cu.ho, cu.wo);
   }
 };
 
@@ -101,18 +185,32 @@ template <int ORDER>
 struct LdWdgrad {
   static constexpr bool kContig = false;  // consecutive k are strided in memory; consecutive rows (c_in) are the near axis
   const float* w; int Cout, KK; long s_co, s_c, s_kk;
+  __device__ __forceinline__ void split_k(int k, int& co, int& kk) const {
+    if (ORDER == ORDER_CKK) { kk = k % KK; co = k / KK; } else { co = k % Cout; kk = k / Cout; }
+  }
   __device__ __forceinline__ float operator()(int, int row, int k) const {
     int co, kk;
-    if (ORDER == ORDER_CKK) { kk = k % KK; co = k / KK; } else { co = k % Cout; kk = k / Cout; }
+    split_k(k, co, kk);
     return __ldg(w + co * s_co + row * s_c + kk * s_kk);
   }
-  __device__ __forceinline__ float4 load4(int b, int row, int k, int kend) const {
-    float4 r;
-    r.x = k < kend ? (*this)(b, row, k) : 0.f;
-    r.y = k + 1 < kend ? (*this)(b, row, k + 1) : 0.f;
-    r.z = k + 2 < kend ? (*this)(b, row, k + 2) : 0.f;
-    r.w = k + 3 < kend ? (*this)(b, row, k + 3) : 0.f;
-    return r;
+  struct Cur { const float* wr; int k, co, kk; };
+  __device__ __forceinline__ Cur cursor(int, int row, int k) const {
+    Cur cu;
+    cu.wr = w + row * s_c; cu.k = k;
+    split_k(k, cu.co, cu.kk);
+    return cu;
+  }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+    int co = cu.co, kk = cu.kk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = (cu.k + i < kend) ? __ldg(cu.wr + co * s_co + kk * s_kk) : 0.f;
+      if (ORDER == ORDER_CKK) { if (++kk == KK) { kk = 0; ++co; } } else { if (++co == Cout) { co = 0; ++kk; } }
+    }
+  }
+  __device__ __forceinline__ void advance(Cur& cu) const {
+    cu.k += LD_STEP;
+    split_k(cu.k, cu.co, cu.kk);
   }
 };
 

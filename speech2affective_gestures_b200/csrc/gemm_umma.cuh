@@ -137,25 +137,22 @@ __device__ __forceinline__ void split_store(const float (&v)[8], unsigned char* 
 }
 
 // Staging items.  An item is (row r of the tile, k-chunk k8 of the 32-wide k-block) = 8 fp32 -> one 16-byte chunk.
-//   k-contiguous operands: id -> (r = id / 4, k8 = id % 4): a warp reads 8 rows x 128 contiguous bytes (two
-//     16-byte loads per thread) and stores 4 x 128 conflict-free bytes;
+//   k-contiguous operands: a warp reads 8 rows x 128 contiguous bytes (two 16-byte loads per thread) and each
+//     lane-octet stores one conflict-free 128-byte group;
 //   row-contiguous operands (transposed views): id -> (r = id % rows, k8 = id / rows): a warp reads 32
 //     consecutive rows per k (coalesced scalar loads) and stores 512 contiguous bytes.
 template <class Ld>
 __device__ __forceinline__ void item_coords(int id, int rows, int& r, int& k8) {
-  if (Ld::kContig) { r = id >> 2; k8 = id & 3; } else { r = id % rows; k8 = id / rows; }
+  // k-contiguous: 8 consecutive lanes take 8 consecutive rows of ONE k-chunk (their 16-byte smem stores fill one
+  // conflict-free 128-byte row group); the 4 lane-octets of a warp take the 4 chunks of the same 8 rows, so a warp
+  // still reads 8 rows x 128 contiguous bytes from global memory.
+  if (Ld::kContig) { r = (id & 7) + ((id >> 5) << 3); k8 = (id >> 3) & 3; } else { r = id % rows; k8 = id / rows; }
 }
 template <class Ld>
-__device__ __forceinline__ void fetch_item(const Ld& ld, int batch, int row, int row_lim, int k, int kend,
+__device__ __forceinline__ void fetch_item(const Ld& ld, const typename Ld::Cur& cur, bool ok, int k, int kend,
                                            float (&v)[8]) {
-  if (row < row_lim && k < kend) {
-    if (Ld::kContig) {
-      const float4 a = ld.load4(batch, row, k, kend), b = ld.load4(batch, row, k + 4, kend);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (k + i < kend) ? ld(batch, row, k + i) : 0.f;
-    }
+  if (ok && k < kend) {
+    ld.load8(cur, kend, v);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -196,44 +193,51 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // staging assignment: two A items and (at most) two B items per thread (see item_coords)
-  int rA[2], kA[2], rB[2], kB[2];
-  bool hasB[2];
+  // staging assignment: two A items and (at most) two B items per thread (see item_coords); one cursor per item
+  static_assert(BK == LD_STEP, "loader cursors advance by one k-block");
+  int offA[2], offB[2];
+  bool okA[2], okB[2];
+  typename LdA::Cur ca[2];
+  typename LdB::Cur cb[2];
+  int kA[2], kB[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    item_coords<LdA>(tid + i * THREADS, BM, rA[i], kA[i]);
-    hasB[i] = tid + i * THREADS < 4 * BN;
-    item_coords<LdB>(hasB[i] ? tid + i * THREADS : 0, BN, rB[i], kB[i]);
+    int r, k8;
+    item_coords<LdA>(tid + i * THREADS, BM, r, k8);
+    okA[i] = m0 + r < M;
+    offA[i] = (k8 * BM + r) * 16;
+    kA[i] = kbeg + k8 * 8;
+    ca[i] = a.cursor(batch, okA[i] ? m0 + r : 0, kA[i]);
+    const bool has = tid + i * THREADS < 4 * BN;
+    item_coords<LdB>(has ? tid + i * THREADS : 0, BN, r, k8);
+    okB[i] = has && n0 + r < N;
+    offB[i] = has ? (k8 * BN + r) * 16 : -1;
+    kB[i] = kbeg + k8 * 8;
+    cb[i] = b.cursor(batch, okB[i] ? n0 + r : 0, kB[i]);
   }
   float va[2][8], vb[2][8], na[2][8], nb[2][8];
-  if (nkb > 0) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      fetch_item(a, batch, m0 + rA[i], M, kbeg + kA[i] * 8, kend, va[i]);
-      if (hasB[i]) fetch_item(b, batch, n0 + rB[i], N, kbeg + kB[i] * 8, kend, vb[i]);
-    }
-  }
   const uint32_t idesc = make_idesc(BN);
   const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
 
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    const bool more = kb + 1 < nkb;
-    if (more) {  // prefetch the next k-block into the second register set
-      const int k0 = kbeg + (kb + 1) * BK;
+  auto fetch = [&](float (&fa)[2][8], float (&fb)[2][8]) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        fetch_item(a, batch, m0 + rA[i], M, k0 + kA[i] * 8, kend, na[i]);
-        if (hasB[i]) fetch_item(b, batch, n0 + rB[i], N, k0 + kB[i] * 8, kend, nb[i]);
+    for (int i = 0; i < 2; ++i) {
+      fetch_item(a, ca[i], okA[i], kA[i], kend, fa[i]);
+      a.advance(ca[i]); kA[i] += BK;
+      if (offB[i] >= 0) {
+        fetch_item(b, cb[i], okB[i], kB[i], kend, fb[i]);
+        b.advance(cb[i]); kB[i] += BK;
       }
     }
+  };
+  auto stage_and_issue = [&](int kb, const float (&fa)[2][8], const float (&fb)[2][8]) {
+    const int s = kb & 1;
     if (kb >= 2) mbar_wait(bar_empty[s], (uint32_t)(((kb >> 1) - 1) & 1));  // MMAs that read stage s are done
     unsigned char* st = stage0 + s * stage_bytes;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      split_store(va[i], st, st + BM * BK * 2, (kA[i] * BM + rA[i]) * 16, x3 != 0);
-      if (hasB[i])
-        split_store(vb[i], st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, (kB[i] * BN + rB[i]) * 16, x3 != 0);
+      split_store(fa[i], st, st + BM * BK * 2, offA[i], x3 != 0);
+      if (offB[i] >= 0) split_store(fb[i], st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[i], x3 != 0);
     }
     fence_async_smem();
     __syncthreads();
@@ -255,13 +259,18 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
         mma_bf16(tmem_base, dah, dbh, idesc, acc);
       }
       mma_commit(bar_empty[s]);
-      if (!more) mma_commit(bar_done);
+      if (kb + 1 == nkb) mma_commit(bar_done);
     }
-    if (more) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { va[i][j] = na[i][j]; vb[i][j] = nb[i][j]; }
+  };
+
+  // two register sets ping-pong: the loads of k-block kb+1 are in flight while k-block kb is converted and issued
+  if (nkb > 0) fetch(va, vb);
+  for (int kb = 0; kb < nkb; kb += 2) {
+    if (kb + 1 < nkb) fetch(na, nb);
+    stage_and_issue(kb, va, vb);
+    if (kb + 1 < nkb) {
+      if (kb + 2 < nkb) fetch(va, vb);
+      stage_and_issue(kb + 1, na, nb);
     }
   }
 
