@@ -33,19 +33,23 @@ struct LdPlain {
   __device__ __forceinline__ float operator()(int b, int row, int k) const {
     return __ldg(p + b * bstride + (long)row * ld_row + (long)k * ld_k);
   }
-  struct Cur { const float* q; int k; };
+  struct Cur { const float* q; int k; bool vec; };
   __device__ __forceinline__ Cur cursor(int b, int row, int k) const {
-    return Cur{p + b * bstride + (long)row * ld_row + (long)k * ld_k, k};
+    const float* q = p + b * bstride + (long)row * ld_row + (long)k * ld_k;
+    return Cur{q, k, KCONTIG && ld_k == 1 && s2ag_aligned16(q)};  // advance() keeps the 16-byte alignment
+  }
+  __device__ __forceinline__ void load8_full(const Cur& c, float (&v)[8]) const {  // all 8 k in range
+    if (c.vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(c.q)), b = __ldg(reinterpret_cast<const float4*>(c.q) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(c.q + i * ld_k);
+    }
   }
   __device__ __forceinline__ void load8(const Cur& c, int kend, float (&v)[8]) const {
     if (c.k + 8 <= kend) {
-      if (KCONTIG && ld_k == 1 && s2ag_aligned16(c.q)) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(c.q)), b = __ldg(reinterpret_cast<const float4*>(c.q) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __ldg(c.q + i * ld_k);
-      }
+      load8_full(c, v);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (c.k + i < kend) ? __ldg(c.q + i * ld_k) : 0.f;
@@ -98,9 +102,10 @@ struct LdConv {
     if (hi < 0 || hi >= H || wi < 0 || wi >= W) return nullptr;
     return cu.xn + ((long)hi * W + wi) * ldpix;
   }
-  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+  template <bool FULL>
+  __device__ __forceinline__ void load8_impl(const Cur& cu, int kend, float (&v)[8]) const {
     int c = cu.c, kh = cu.kh, kw = cu.kw;
-    if (ORDER == ORDER_KKC && (C & 3) == 0 && cu.k + 8 <= kend) {
+    if (ORDER == ORDER_KKC && (C & 3) == 0 && (FULL || cu.k + 8 <= kend)) {
       // two groups of 4 channels, each inside one pixel (k % 4 == 0 and C % 4 == 0)
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -124,7 +129,7 @@ struct LdConv {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float val = 0.f;
-      if (cu.k + i < kend) {
+      if (FULL || cu.k + i < kend) {
         const float* q = pix(cu, kh, kw);
         if (q) val = __ldg(q + c);
       }
@@ -133,6 +138,8 @@ struct LdConv {
       else { if (++c == C) { c = 0; if (++kw == KW) { kw = 0; ++kh; } } }
     }
   }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const { load8_impl<false>(cu, kend, v); }
+  __device__ __forceinline__ void load8_full(const Cur& cu, float (&v)[8]) const { load8_impl<true>(cu, 0, v); }
   __device__ __forceinline__ void advance(Cur& cu) const {
     cu.k += LD_STEP;
     if (ORDER == ORDER_KKC) {
@@ -159,13 +166,14 @@ struct LdT {
     l.split_row(k, cu.n, cu.ho, cu.wo);
     return cu;
   }
-  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+  template <bool FULL>
+  __device__ __forceinline__ void load8_impl(const Cur& cu, int kend, float (&v)[8]) const {
     int n = cu.n, ho = cu.ho, wo = cu.wo;
     const int dhh = l.sgn * cu.kh * l.dh + l.off_h, dww = l.sgn * cu.kw * l.dw + l.off_w;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float val = 0.f;
-      if (cu.p + i < kend) {
+      if (FULL || cu.p + i < kend) {
         const int hi = ho * l.sh + dhh, wi = wo * l.sw + dww;
         if (hi >= 0 && hi < l.H && wi >= 0 && wi < l.W) val = __ldg(l.x + ((long)(n * l.H + hi) * l.W + wi) * l.ldpix + cu.c);
       }
@@ -173,6 +181,8 @@ struct LdT {
       if (++wo == l.Wo) { wo = 0; if (++ho == l.Ho) { ho = 0; ++n; } }
     }
   }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const { load8_impl<false>(cu, kend, v); }
+  __device__ __forceinline__ void load8_full(const Cur& cu, float (&v)[8]) const { load8_impl<true>(cu, 0, v); }
   __device__ __forceinline__ void advance(Cur& cu) const {
     cu.p += LD_STEP;
     l.split_row(cu.p, cu.n, cu.ho, cu.wo);
@@ -200,14 +210,17 @@ struct LdWdgrad {
     split_k(k, cu.co, cu.kk);
     return cu;
   }
-  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const {
+  template <bool FULL>
+  __device__ __forceinline__ void load8_impl(const Cur& cu, int kend, float (&v)[8]) const {
     int co = cu.co, kk = cu.kk;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      v[i] = (cu.k + i < kend) ? __ldg(cu.wr + co * s_co + kk * s_kk) : 0.f;
+      v[i] = (FULL || cu.k + i < kend) ? __ldg(cu.wr + co * s_co + kk * s_kk) : 0.f;
       if (ORDER == ORDER_CKK) { if (++kk == KK) { kk = 0; ++co; } } else { if (++co == Cout) { co = 0; ++kk; } }
     }
   }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const { load8_impl<false>(cu, kend, v); }
+  __device__ __forceinline__ void load8_full(const Cur& cu, float (&v)[8]) const { load8_impl<true>(cu, 0, v); }
   __device__ __forceinline__ void advance(Cur& cu) const {
     cu.k += LD_STEP;
     split_k(cu.k, cu.co, cu.kk);

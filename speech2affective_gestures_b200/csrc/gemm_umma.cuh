@@ -10,10 +10,10 @@
 // tensor core accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  in fp32 in TMEM ("bf16x3", ~2^-17
 // relative operand error).  precision mode 1 ("bf16x1") drops the two correction terms.
 //
-// Structure of one CTA (256 threads, one 128 x BN output tile, BN <= 128 a multiple of 16):
-//   - all 8 warps stage: global -> registers (next k-block prefetched while the current one is
-//     converted) -> bf16 hi/lo -> shared memory in the canonical no-swizzle K-major UMMA layout
-//     [k-chunk of 8][row][16 B], two stages;
+// Structure of one CTA (512 threads, one 128 x BN output tile, BN <= 256 a multiple of 16):
+//   - all 16 warps stage: global -> registers (three rotating register sets: the loads of the next TWO
+//     k-blocks are in flight while the current one is converted) -> bf16 hi/lo -> shared memory in the
+//     canonical no-swizzle K-major UMMA layout [k-chunk of 8][row][16 B], two stages;
 //   - fence.proxy.async + __syncthreads, then ONE thread issues the tcgen05.mma instructions of the
 //     stage (M=128, N=BN, K=16 each) and tcgen05.commit's the stage's "empty" mbarrier, so the
 //     tensor core works on stage s while the warps stage s^1;
@@ -29,7 +29,7 @@
 namespace s2ag {
 namespace umma {
 
-constexpr int BM = 128, BK = 32, THREADS = 256;
+constexpr int BM = 128, BK = 32, THREADS = 512, BN_MAX = 256, EPI_WARPS = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2 * 2;  // hi + lo, bf16
 constexpr int HEADER_BYTES = 128;               // mbarriers + TMEM base slot
 
@@ -148,20 +148,22 @@ __device__ __forceinline__ void item_coords(int id, int rows, int& r, int& k8) {
   // still reads 8 rows x 128 contiguous bytes from global memory.
   if (Ld::kContig) { r = (id & 7) + ((id >> 5) << 3); k8 = (id >> 3) & 3; } else { r = id % rows; k8 = id / rows; }
 }
-template <class Ld>
+template <bool FULL, class Ld>
 __device__ __forceinline__ void fetch_item(const Ld& ld, const typename Ld::Cur& cur, bool ok, int k, int kend,
                                            float (&v)[8]) {
-  if (ok && k < kend) {
-    ld.load8(cur, kend, v);
+  if (ok && (FULL || k < kend)) {
+    if (FULL) ld.load8_full(cur, v); else ld.load8(cur, kend, v);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
   }
 }
 
+struct RegSet { float a[8]; float b0[8]; float b1[8]; };
+
 template <class LdA, class LdB, class Epi>
-__global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi epi, int M, int N, int K, int splitk,
-                                                            int BN, int x3) {
+__global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi epi, int M, int N, int K, int splitk,
+                                                               int BN, int x3) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
   const int kbeg = ks * kper;
   const int kend = (kbeg + kper < K) ? kbeg + kper : K;
   const int nkb = kbeg < kend ? (kend - kbeg + BK - 1) / BK : 0;
-  const uint32_t ncols = BN <= 32 ? 32u : (BN <= 64 ? 64u : 128u);
+  const bool tail_full = ((kend - kbeg) & (BK - 1)) == 0;
+  const uint32_t ncols = BN <= 32 ? 32u : (BN <= 64 ? 64u : (BN <= 128 ? 128u : 256u));
 
   if (tid == 0) {
     mbar_init(bar_empty[0], 1);
@@ -193,21 +196,19 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // staging assignment: two A items and (at most) two B items per thread (see item_coords); one cursor per item
+  // staging assignment: one A item and up to two B items per thread (see item_coords); one cursor per item
   static_assert(BK == LD_STEP, "loader cursors advance by one k-block");
-  int offA[2], offB[2];
-  bool okA[2], okB[2];
-  typename LdA::Cur ca[2];
+  int r, k8;
+  item_coords<LdA>(tid, BM, r, k8);
+  const bool okA = m0 + r < M;
+  const int offA = (k8 * BM + r) * 16;
+  int kA = kbeg + k8 * 8;
+  typename LdA::Cur ca = a.cursor(batch, okA ? m0 + r : 0, kA);
+  int offB[2], kB[2];
+  bool okB[2];
   typename LdB::Cur cb[2];
-  int kA[2], kB[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    int r, k8;
-    item_coords<LdA>(tid + i * THREADS, BM, r, k8);
-    okA[i] = m0 + r < M;
-    offA[i] = (k8 * BM + r) * 16;
-    kA[i] = kbeg + k8 * 8;
-    ca[i] = a.cursor(batch, okA[i] ? m0 + r : 0, kA[i]);
     const bool has = tid + i * THREADS < 4 * BN;
     item_coords<LdB>(has ? tid + i * THREADS : 0, BN, r, k8);
     okB[i] = has && n0 + r < N;
@@ -215,30 +216,31 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
     kB[i] = kbeg + k8 * 8;
     cb[i] = b.cursor(batch, okB[i] ? n0 + r : 0, kB[i]);
   }
-  float va[2][8], vb[2][8], na[2][8], nb[2][8];
   const uint32_t idesc = make_idesc(BN);
   const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
 
-  auto fetch = [&](float (&fa)[2][8], float (&fb)[2][8]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      fetch_item(a, ca[i], okA[i], kA[i], kend, fa[i]);
-      a.advance(ca[i]); kA[i] += BK;
-      if (offB[i] >= 0) {
-        fetch_item(b, cb[i], okB[i], kB[i], kend, fb[i]);
-        b.advance(cb[i]); kB[i] += BK;
-      }
+  auto fetch = [&](int kb, RegSet& s) {
+    if (kb >= nkb) return;
+    if (kb + 1 < nkb || tail_full) {
+      fetch_item<true>(a, ca, okA, kA, kend, s.a);
+      if (offB[0] >= 0) fetch_item<true>(b, cb[0], okB[0], kB[0], kend, s.b0);
+      if (offB[1] >= 0) fetch_item<true>(b, cb[1], okB[1], kB[1], kend, s.b1);
+    } else {
+      fetch_item<false>(a, ca, okA, kA, kend, s.a);
+      if (offB[0] >= 0) fetch_item<false>(b, cb[0], okB[0], kB[0], kend, s.b0);
+      if (offB[1] >= 0) fetch_item<false>(b, cb[1], okB[1], kB[1], kend, s.b1);
     }
+    a.advance(ca); kA += BK;
+    b.advance(cb[0]); kB[0] += BK;
+    b.advance(cb[1]); kB[1] += BK;
   };
-  auto stage_and_issue = [&](int kb, const float (&fa)[2][8], const float (&fb)[2][8]) {
-    const int s = kb & 1;
-    if (kb >= 2) mbar_wait(bar_empty[s], (uint32_t)(((kb >> 1) - 1) & 1));  // MMAs that read stage s are done
-    unsigned char* st = stage0 + s * stage_bytes;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      split_store(fa[i], st, st + BM * BK * 2, offA[i], x3 != 0);
-      if (offB[i] >= 0) split_store(fb[i], st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[i], x3 != 0);
-    }
+  auto stage_and_issue = [&](int kb, const RegSet& s) {
+    const int st_i = kb & 1;
+    if (kb >= 2) mbar_wait(bar_empty[st_i], (uint32_t)(((kb >> 1) - 1) & 1));  // MMAs that read this stage are done
+    unsigned char* st = stage0 + st_i * stage_bytes;
+    split_store(s.a, st, st + BM * BK * 2, offA, x3 != 0);
+    if (offB[0] >= 0) split_store(s.b0, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[0], x3 != 0);
+    if (offB[1] >= 0) split_store(s.b1, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[1], x3 != 0);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -258,19 +260,25 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
         }
         mma_bf16(tmem_base, dah, dbh, idesc, acc);
       }
-      mma_commit(bar_empty[s]);
+      mma_commit(bar_empty[st_i]);
       if (kb + 1 == nkb) mma_commit(bar_done);
     }
   };
 
-  // two register sets ping-pong: the loads of k-block kb+1 are in flight while k-block kb is converted and issued
-  if (nkb > 0) fetch(va, vb);
-  for (int kb = 0; kb < nkb; kb += 2) {
-    if (kb + 1 < nkb) fetch(na, nb);
-    stage_and_issue(kb, va, vb);
+  // three register sets rotate: the loads of k-blocks kb+1 and kb+2 are in flight while k-block kb is converted
+  RegSet s0, s1, s2;
+  fetch(0, s0);
+  fetch(1, s1);
+  for (int kb = 0; kb < nkb; kb += 3) {
+    fetch(kb + 2, s2);
+    stage_and_issue(kb, s0);
     if (kb + 1 < nkb) {
-      if (kb + 2 < nkb) fetch(va, vb);
-      stage_and_issue(kb + 1, na, nb);
+      fetch(kb + 3, s0);
+      stage_and_issue(kb + 1, s1);
+    }
+    if (kb + 2 < nkb) {
+      fetch(kb + 4, s1);
+      stage_and_issue(kb + 2, s2);
     }
   }
 
@@ -280,17 +288,19 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
     // epilogue: the stage buffers are free now (every MMA has completed); reuse them for the transposition
     float* tbuf = reinterpret_cast<float*>(stage0) + warp * (32 * 33);
     const int lane_base = (warp & 3) * 32;
-    for (int c0 = (warp >> 2) * 32; c0 < BN; c0 += 64) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+    for (int c0 = (warp >> 2) * 32; c0 < BN; c0 += 32 * (EPI_WARPS / 4)) {
+      uint32_t rr32[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, rr32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(rr32[j]);
       __syncwarp();
       const int n = n0 + c0 + lane;
       const bool n_ok = (c0 + lane < BN) && n < N;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = m0 + lane_base + rr;
-        if (m < M && n_ok) epi(batch, m, n, tbuf[rr * 33 + lane], splitk > 1);
+      const int mlim = M - (m0 + lane_base);
+      if (n_ok) {
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr)
+          if (rr < mlim) epi(batch, m0 + lane_base + rr, n, tbuf[rr * 33 + lane], splitk > 1);
       }
       __syncwarp();
     }
@@ -301,35 +311,45 @@ __global__ void __launch_bounds__(THREADS) gemm_umma_kernel(LdA a, LdB b, Epi ep
 }
 
 static inline int pick_bn(int N) {
-  int tiles = (N + 127) / 128;
+  int tiles = (N + BN_MAX - 1) / BN_MAX;
   int bn = (N + tiles - 1) / tiles;
   bn = ((bn + 15) / 16) * 16;
   if (bn < 16) bn = 16;
-  if (bn > 128) bn = 128;
+  if (bn > BN_MAX) bn = BN_MAX;
   return bn;
 }
 static inline size_t smem_bytes(int BN) {
   size_t stages = 2 * (size_t)(A_STAGE_BYTES + 2 * BN * BK * 2);
-  size_t epi = 8 * 32 * 33 * sizeof(float);
+  size_t epi = EPI_WARPS * 32 * 33 * sizeof(float);
   return HEADER_BYTES + (stages > epi ? stages : epi);
 }
 
+// splitk > 1 on entry means "the epilogue is linear, partial sums may be combined by atomicAdd": the engine then
+// picks its own split so that one wave of CTAs (one per SM) covers the problem.
 template <class LdA, class LdB, class Epi>
 static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
                           void* stream) {
   auto kfn = &gemm_umma_kernel<LdA, LdB, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128));
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(BN_MAX));
     attr_set = true;
   }
   const int BN = pick_bn(N);
+  const int tiles = s2ag_cdiv(N, BN) * s2ag_cdiv(M, BM) * nbatch;
+  if (splitk > 1) {
+    int sk = 148 / tiles;
+    const int maxk = K / (4 * BK);
+    if (sk > maxk) sk = maxk;
+    if (sk < 1) sk = 1;
+    splitk = sk;
+  }
   dim3 grid(s2ag_cdiv(N, BN), s2ag_cdiv(M, BM), nbatch * splitk);
   S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0);
 }
 
 // shapes worth a tensor-core tile: anything else stays on the exact-fp32 SIMT kernel
-static inline bool worthwhile(int M, int N, int K) { return M >= 64 && N >= 16 && K >= 32; }
+static inline bool worthwhile(int M, int N, int K) { return M >= 8 && N >= 16 && K >= 32; }
 
 }  // namespace umma
 }  // namespace s2ag
