@@ -43,6 +43,9 @@ int s2ag_set_engine(int engine);
 int s2ag_set_precision(int mode);
 /* reserved for bring-up experiments of the tcgen05 kernels */
 int s2ag_debug_flags(int flags);
+/* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
+ * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */
+int s2ag_debug_read_timeline(long long* host, int n);
 
 #define S2AG_ACT_NONE 0
 #define S2AG_ACT_RELU 1

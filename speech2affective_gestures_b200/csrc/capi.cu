@@ -31,6 +31,16 @@ extern "C" int s2ag_set_precision(int mode) {
 #endif
   return S2AG_OK;
 }
+#ifndef S2AG_EMU
+namespace s2ag { int gru_debug_read_timeline(long long* host, int n); }
+#endif
+extern "C" int s2ag_debug_read_timeline(long long* host, int n) {
+#ifndef S2AG_EMU
+  return s2ag::gru_debug_read_timeline(host, n);
+#else
+  (void)host; (void)n; return S2AG_ERR_UNSUPPORTED;
+#endif
+}
 extern "C" int s2ag_debug_flags(int flags) {
 #ifndef S2AG_EMU
   s2ag::umma::g_dbg_flags = flags;

@@ -38,6 +38,7 @@ struct Params {
   unsigned char* xchg;      // operand images: [group][parity][hi|lo][Kpad/8][128][16 B]
   unsigned int* cnt;        // one arrival counter per group, 32 words apart
   int B, T, H, Kpad, S, nbt, bt0, x3;  // nbt: batch tiles of the whole batch; bt0: first tile of this launch
+  int dbg;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -55,6 +56,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
+// same without the wait: the destination registers are valid only after tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
 __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -68,33 +79,59 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(PTHREADS, 1) gru_persist_fwd_kernel(Params p) {
+// Forward kernel: 9 warps.  Warps 0-7 ("workers", thread = clip row x 8 hidden units) fetch the operand image
+// slice by slice as the producing CTAs publish it (per-slice release/acquire flags, cp.async.cg + mbarrier
+// arrive-on-completion) and run the gate-math epilogue; warp 8 issues the tcgen05.mma k-step of a slice as soon as
+// that slice has landed, so only the LAST slice to arrive is on the critical path of a time step.
+constexpr int FWD_THREADS = 384, FWD_HDR = 512, MAX_SLICES = 24, NISSUE = 4;  // 8 worker warps + 4 MMA-issuer warps
+// Back-to-back tcgen05.mma into ONE accumulator serialise on the MMA latency (~160 cycles each for these tiny N=48
+// tiles, measured): the k-steps of a time step are spread round-robin over NACC independent TMEM accumulators that
+// the epilogue sums.
+constexpr int NACC = 8;  // = 2 per MMA-issuer thread
+
+// bring-up aid (s2ag_debug_flags bit 1): clock64 timeline of CTA (slice 0, tile 0, direction 0), 16 marks per step
+__device__ long long g_gru_timeline[64 * 16];
+__device__ long long g_gru_slices[64 * 3 * MAX_SLICES];  // per step: [flag seen | copy issued | landed][slice]
+#define GRU_MARK(slot) do { if (dbg) g_gru_timeline[(s & 63) * 16 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
-  const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad;
+  const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad, S = p.S;
   const int nchunk = Kpad >> 3;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t mma_bar = sbase;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8);
-  unsigned char* w_hi = smem + HDR;                   // [nchunk][48][16]
+  const uint32_t mma_bar = sbase;            // all MMAs of a step have completed
+  const uint32_t tfree_bar = sbase + 8;      // the 8 worker warps have read the accumulator of the previous step
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 16);
+  const uint32_t ready0 = sbase + 64;        // ready[kk]: slice kk of the operand image has landed (TMA complete_tx)
+  unsigned char* w_hi = smem + FWD_HDR;                // [nchunk][48][16]
   unsigned char* w_lo = w_hi + nchunk * NC * 16;
-  unsigned char* a_hi = w_lo + nchunk * NC * 16;      // [nchunk][128][16]
+  unsigned char* a_hi = w_lo + nchunk * NC * 16;       // [nchunk][128][16]
   const int a_half = nchunk * PBM * 16;
   const int group = dir * p.nbt + bt;
-  const unsigned* cnt = p.cnt + group * 32;
+  unsigned* flags = p.cnt + (size_t)group * MAX_SLICES * 32;   // one flag per slice, 128 bytes apart
   unsigned char* img0 = p.xchg + (size_t)group * 2 * (2 * (size_t)a_half);
 
   if (tid == 0) {
-    mbar_init(mma_bar, 1);
+    mbar_init(mma_bar, NISSUE);
+    mbar_init(tfree_bar, 8);
+    for (int i = 0; i < S; ++i) mbar_init(ready0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(sbase + 8, 64);
+  if (warp == 0) tmem_alloc(sbase + 16, 512);
 
   // ---- stationary W_hh slice: rows n = g*16 + jj  <->  W_hh[g*H + j0 + jj][k]
   const float* whh = p.whh + dir * p.whh_dstride;
   const int j0 = slice * HS;
-  for (int idx = tid; idx < nchunk * NC; idx += PTHREADS) {
+  for (int idx = tid; idx < nchunk * NC; idx += FWD_THREADS) {
     const int n = idx % NC, kc = idx / NC;
     const int g = n / HS, j = j0 + n % HS;
     float v[8];
@@ -108,153 +145,238 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_fwd_kernel(Params p) 
     *reinterpret_cast<uint4*>(w_hi + (kc * NC + n) * 16) = hi;
     *reinterpret_cast<uint4*>(w_lo + (kc * NC + n) * 16) = lo;
   }
-
-  // ---- per-thread epilogue assignment: clip row, 8 hidden units
-  const int row = (warp & 3) * 32 + lane;
-  const int b = bt * PBM + row;
-  const int u0 = (warp >> 2) * 8;          // unit offset inside the slice
-  const int jb = j0 + u0;                  // first hidden unit of this thread
-  const bool b_ok = b < B;
-  // 16-byte accesses to gi / out rows: all 8 units valid and every row segment 16-byte aligned
-  const bool vec_ok = (H & 3) == 0 && jb + 8 <= H && ((reinterpret_cast<uintptr_t>(p.gi) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
-  const float* bhh = p.bhh + dir * p.bhh_dstride;
-  float br[8], bz[8], bn[8], h_own[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool ok = jb + i < H;
-    br[i] = ok ? __ldg(bhh + jb + i) : 0.f;
-    bz[i] = ok ? __ldg(bhh + H + jb + i) : 0.f;
-    bn[i] = ok ? __ldg(bhh + 2 * H + jb + i) : 0.f;
-    h_own[i] = 0.f;
-  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = make_idesc(NC);
-  const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
-  for (int s = 0; s < T; ++s) {
-    const int t = dir == 0 ? s : T - 1 - s;
-    // gi of this step: independent of the recurrence, issue the loads first
-    float gr[8], gz[8], gn[8];
-    {
-      const float* g = p.gi + ((long)(b_ok ? b : 0) * T + t) * 6 * H + (long)dir * 3 * H + jb;
-      if (vec_ok) {
-        if (b_ok) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(g)), r1 = __ldg(reinterpret_cast<const float4*>(g) + 1);
-          const float4 z0 = __ldg(reinterpret_cast<const float4*>(g + H)), z1 = __ldg(reinterpret_cast<const float4*>(g + H) + 1);
-          const float4 n0 = __ldg(reinterpret_cast<const float4*>(g + 2 * H)), n1 = __ldg(reinterpret_cast<const float4*>(g + 2 * H) + 1);
-          gr[0] = r0.x; gr[1] = r0.y; gr[2] = r0.z; gr[3] = r0.w; gr[4] = r1.x; gr[5] = r1.y; gr[6] = r1.z; gr[7] = r1.w;
-          gz[0] = z0.x; gz[1] = z0.y; gz[2] = z0.z; gz[3] = z0.w; gz[4] = z1.x; gz[5] = z1.y; gz[6] = z1.z; gz[7] = z1.w;
-          gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gr[i] = gz[i] = gn[i] = 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = b_ok && jb + i < H;
-          gr[i] = ok ? __ldg(g + i) : 0.f;
-          gz[i] = ok ? __ldg(g + H + i) : 0.f;
-          gn[i] = ok ? __ldg(g + 2 * H + i) : 0.f;
-        }
-      }
-    }
-    float ar[8], az[8], an[8];
-    if (s > 0) {
-      // all S slices of this (tile, direction) have published h_{s-1}
-      if (tid == 0) {
-        const unsigned target = (unsigned)p.S * (unsigned)s;
-        unsigned spins = 0;
-        while (ld_acquire_u32(cnt) < target) {
-          if (++spins > (1u << 26)) __trap();
-        }
-        __threadfence();
-      }
-      __syncthreads();
-      // operand image (parity (s-1)&1): L2 -> shared memory, 16-byte cp.async.cg (L1 bypassed, no register staging)
-      {
-        const unsigned char* src = img0 + (size_t)((s - 1) & 1) * 2 * a_half;
-        const uint32_t dst = smem_u32(a_hi);
-        const int nbytes = (p.x3 ? 2 : 1) * a_half;
-        for (int off = tid * 16; off < nbytes; off += PTHREADS * 16)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
+  const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (warp >= 8) {
+    // ================================ MMA issuers ================================
+    // One lane of each of the NISSUE issuer warps takes the k-steps kk = iss, iss + NISSUE, ... (a single thread
+    // executes the ~dozens of dependent scalar instructions around each tcgen05.mma at only one every few cycles:
+    // four issue streams keep the tail after the last slice short) and accumulates into its own two TMEM
+    // accumulators; each issuer commits to mma_bar (NISSUE arrivals).
+    if (lane == 0) {
+      const int iss = warp - 8;
+      const bool dbg = dbg_cta && iss == 0;
+      const uint32_t idesc = make_idesc(NC);
+      const uint32_t a_lbo = PBM * 16, w_lbo = NC * 16;
+      const uint64_t dah0 = make_desc(smem_u32(a_hi), a_lbo, 128), dal0 = make_desc(smem_u32(a_hi) + a_half, a_lbo, 128);
+      const uint64_t dwh0 = make_desc(smem_u32(w_hi), w_lbo, 128), dwl0 = make_desc(smem_u32(w_lo), w_lbo, 128);
+      const uint32_t acc0 = tmem_base + (uint32_t)(2 * iss * NC), acc1 = acc0 + NC;
+      for (int s = 1; s < T; ++s) {
+        const uint32_t par = (uint32_t)((s - 1) & 1);
+        mbar_wait(tfree_bar, par);  // accumulators of step s-1 have been read by every worker warp
         tc_fence_after();
-        const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
-        const uint32_t a_lbo = PBM * 16, w_lbo = NC * 16;
-        for (int kk = 0; kk < (Kpad >> 4); ++kk) {
-          const uint32_t ah = sa + kk * 2 * a_lbo, al = ah + a_half;
-          const uint32_t wh = sw + kk * 2 * w_lbo, wl = wh + nchunk * NC * 16;
-          const uint64_t dah = make_desc(ah, a_lbo, 128), dwh = make_desc(wh, w_lbo, 128);
-          uint32_t acc = kk > 0 ? 1u : 0u;
+        GRU_MARK(8);
+        uint32_t c = 0;  // MMAs issued by this thread in this step
+        for (int kk = iss; kk < S; kk += NISSUE) {
+          mbar_wait(ready0 + 8 * kk, par);
+          if (dbg) g_gru_slices[((s & 63) * 3 + 2) * MAX_SLICES + kk] = clock64();
+          tc_fence_after();
+          // descriptors of k-step kk: the start-address field (16-byte units) advances by two k-chunks
+          const uint64_t dah = dah0 + (uint64_t)(kk * ((2 * a_lbo) >> 4)), dal = dal0 + (uint64_t)(kk * ((2 * a_lbo) >> 4));
+          const uint64_t dwh = dwh0 + (uint64_t)(kk * ((2 * w_lbo) >> 4)), dwl = dwl0 + (uint64_t)(kk * ((2 * w_lbo) >> 4));
           if (p.x3) {
-            mma_bf16(tmem_base, make_desc(al, a_lbo, 128), dwh, idesc, acc);
-            mma_bf16(tmem_base, dah, make_desc(wl, w_lbo, 128), idesc, 1u);
-            acc = 1u;
+            mma_bf16((c & 1) ? acc1 : acc0, dal, dwh, idesc, c >= 2 ? 1u : 0u); ++c;
+            mma_bf16((c & 1) ? acc1 : acc0, dah, dwl, idesc, c >= 2 ? 1u : 0u); ++c;
           }
-          mma_bf16(tmem_base, dah, dwh, idesc, acc);
+          mma_bf16((c & 1) ? acc1 : acc0, dah, dwh, idesc, c >= 2 ? 1u : 0u); ++c;
         }
         mma_commit(mma_bar);
+        GRU_MARK(11);
       }
-      mbar_wait(mma_bar, (uint32_t)((s - 1) & 1));
-      tc_fence_after();
-      tmem_ld8(t_lane + (uint32_t)(0 * HS + u0), ar);
-      tmem_ld8(t_lane + (uint32_t)(1 * HS + u0), az);
-      tmem_ld8(t_lane + (uint32_t)(2 * HS + u0), an);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ar[i] = az[i] = an[i] = 0.f;
     }
-    // gate math + stores
-    float* orow = p.out + ((long)(b_ok ? b : 0) * T + t) * 2 * H + (long)dir * H + jb;
+  } else {
+    // ================================ workers ================================
+    const int row = (warp & 3) * 32 + lane;
+    const int b = bt * PBM + row;
+    const int u0 = (warp >> 2) * 8;          // unit offset inside the slice
+    const int jb = j0 + u0;                  // first hidden unit of this thread
+    const bool b_ok = b < B;
+    // 16-byte accesses to gi / out rows: all 8 units valid and every row segment 16-byte aligned
+    const bool vec_ok = (H & 3) == 0 && jb + 8 <= H &&
+                        ((reinterpret_cast<uintptr_t>(p.gi) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    const float* bhh = p.bhh + dir * p.bhh_dstride;
+    float br[8], bz[8], bn[8], h_own[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const bool ok = b_ok && jb + i < H;
-      const float ghn = an[i] + bn[i];
-      const float r = s2ag_sigmoid(gr[i] + ar[i] + br[i]);
-      const float z = s2ag_sigmoid(gz[i] + az[i] + bz[i]);
-      const float n = tanhf(gn[i] + r * ghn);
-      const float h = (1.f - z) * n + z * h_own[i];
-      h_own[i] = ok ? h : 0.f;
-      if (ok) {
-        if (!vec_ok) orow[i] = h;
-        if (p.gates) {
-          float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + (jb + i)) * B + b;
-          const long gstride = (long)H * B;
-          gs[0] = r; gs[gstride] = z; gs[2 * gstride] = n; gs[3 * gstride] = ghn;
+      const bool ok = jb + i < H;
+      br[i] = ok ? __ldg(bhh + jb + i) : 0.f;
+      bz[i] = ok ? __ldg(bhh + H + jb + i) : 0.f;
+      bn[i] = ok ? __ldg(bhh + 2 * H + jb + i) : 0.f;
+      h_own[i] = 0.f;
+    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    // accumulator a = 2*issuer + j is written in a step iff that issuer issues more than j MMAs
+    unsigned acc_mask = 0;
+#pragma unroll
+    for (int i = 0; i < NISSUE; ++i) {
+      const int nk = i < S ? (S - i + NISSUE - 1) / NISSUE : 0;
+      const int nm = nk * (p.x3 ? 3 : 1);
+      if (nm > 0) acc_mask |= 1u << (2 * i);
+      if (nm > 1) acc_mask |= 2u << (2 * i);
+    }
+    const bool dbg = dbg_cta && tid == 0;
+    float ph[8], pr[8], pz[8], pn[8], pg[8];
+    int pt = -1;
+    auto store_prev = [&]() {
+      if (pt < 0 || !b_ok) { pt = -1; return; }
+      float* orow = p.out + ((long)b * T + pt) * 2 * H + (long)dir * H + jb;
+      if (vec_ok) {
+        reinterpret_cast<float4*>(orow)[0] = make_float4(ph[0], ph[1], ph[2], ph[3]);
+        reinterpret_cast<float4*>(orow)[1] = make_float4(ph[4], ph[5], ph[6], ph[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (jb + i < H) orow[i] = ph[i];
+      }
+      if (p.gates) {
+        float* gs = p.gates + ((((long)pt * 2 + dir) * 4) * H + jb) * B + b;
+        const long gstride = (long)H * B;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (jb + i < H) {
+            gs[(long)i * B] = pr[i]; gs[gstride + (long)i * B] = pz[i]; gs[2 * gstride + (long)i * B] = pn[i];
+            gs[3 * gstride + (long)i * B] = pg[i];
+          }
         }
       }
-    }
-    if (vec_ok && b_ok) {
-      reinterpret_cast<float4*>(orow)[0] = make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
-      reinterpret_cast<float4*>(orow)[1] = make_float4(h_own[4], h_own[5], h_own[6], h_own[7]);
-    }
-    if (s + 1 < T) {
-      // publish the operand image of h_s (parity s&1): chunk (jb/8), row `row`
-      uint4 hi, lo;
-      pack8(h_own, hi, lo);
-      unsigned char* img = img0 + (size_t)(s & 1) * 2 * a_half;
-      const int off = ((jb >> 3) * PBM + row) * 16;
-      *reinterpret_cast<uint4*>(img + off) = hi;
-      if (p.x3) *reinterpret_cast<uint4*>(img + a_half + off) = lo;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (s + 1 < T && tid == 0) {
-      __threadfence();
-      atomicAdd(const_cast<unsigned*>(cnt), 1u);
+      pt = -1;
+    };
+
+    for (int s = 0; s < T; ++s) {
+      const int t = dir == 0 ? s : T - 1 - s;
+      GRU_MARK(0);
+      // gi of this step: independent of the recurrence, issue the loads first
+      float gr[8], gz[8], gn[8];
+      {
+        const float* g = p.gi + ((long)(b_ok ? b : 0) * T + t) * 6 * H + (long)dir * 3 * H + jb;
+        if (vec_ok) {
+          if (b_ok) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(g)), r1 = __ldg(reinterpret_cast<const float4*>(g) + 1);
+            const float4 z0 = __ldg(reinterpret_cast<const float4*>(g + H)), z1 = __ldg(reinterpret_cast<const float4*>(g + H) + 1);
+            const float4 n0 = __ldg(reinterpret_cast<const float4*>(g + 2 * H)), n1 = __ldg(reinterpret_cast<const float4*>(g + 2 * H) + 1);
+            gr[0] = r0.x; gr[1] = r0.y; gr[2] = r0.z; gr[3] = r0.w; gr[4] = r1.x; gr[5] = r1.y; gr[6] = r1.z; gr[7] = r1.w;
+            gz[0] = z0.x; gz[1] = z0.y; gz[2] = z0.z; gz[3] = z0.w; gz[4] = z1.x; gz[5] = z1.y; gz[6] = z1.z; gz[7] = z1.w;
+            gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gr[i] = gz[i] = gn[i] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = b_ok && jb + i < H;
+            gr[i] = ok ? __ldg(g + i) : 0.f;
+            gz[i] = ok ? __ldg(g + H + i) : 0.f;
+            gn[i] = ok ? __ldg(g + 2 * H + i) : 0.f;
+          }
+        }
+      }
+      float ar[8], az[8], an[8];
+      if (s > 0) {
+        // fetch the operand image slice by slice as soon as each producer has published h_{s-1}: lanes 0..2 of every
+        // worker warp own one slice each (rotated by the CTA's slice index), poll its flag and launch TMA bulk copies
+        // (hi and lo k-chunk pairs, 4096 contiguous bytes each) that complete on the slice's mbarrier.
+        {
+          const int my_i = warp + 8 * lane;
+          if (lane < 3 && my_i < S) {
+            const int sl = (my_i + slice) % S;
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile unsigned*>(flags + sl * 32) < (unsigned)s) {
+              if (++spins > (1u << 26)) __trap();
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            GRU_MARK(1);
+            if (dbg_cta) g_gru_slices[((s & 63) * 3 + 0) * MAX_SLICES + sl] = clock64();
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes (other SMs) -> async-proxy read
+            const unsigned char* src = img0 + (size_t)((s - 1) & 1) * 2 * a_half + (size_t)sl * 2 * PBM * 16;
+            const uint32_t dst = smem_u32(a_hi) + (uint32_t)(sl * 2 * PBM * 16);
+            const uint32_t bar = ready0 + 8 * sl;
+            const uint32_t nbytes = 2 * PBM * 16;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.x3 ? 2 * nbytes : nbytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"(nbytes), "r"(bar)
+                         : "memory");
+            if (p.x3)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                               dst + (uint32_t)a_half),
+                           "l"(src + a_half), "r"(nbytes), "r"(bar)
+                           : "memory");
+            if (dbg_cta) g_gru_slices[((s & 63) * 3 + 1) * MAX_SLICES + sl] = clock64();
+          }
+          __syncwarp();
+        }
+        // layer output and saved gates of the PREVIOUS step: issued while the image is in flight
+        store_prev();
+        GRU_MARK(2);
+        mbar_wait(mma_bar, (uint32_t)((s - 1) & 1));
+        GRU_MARK(3);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ar[i] = az[i] = an[i] = 0.f;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          if (acc_mask & (1u << a)) {
+            float v0[8], v1[8], v2[8];
+            tmem_ld8_nowait(t_lane + (uint32_t)(a * NC + 0 * HS + u0), v0);
+            tmem_ld8_nowait(t_lane + (uint32_t)(a * NC + 1 * HS + u0), v1);
+            tmem_ld8_nowait(t_lane + (uint32_t)(a * NC + 2 * HS + u0), v2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ar[i] += v0[i]; az[i] += v1[i]; an[i] += v2[i]; }
+          }
+        }
+        GRU_MARK(4);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ar[i] = az[i] = an[i] = 0.f;
+      }
+      // the accumulator may be overwritten by the next step's MMAs once every worker warp got here
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && s + 1 < T) mbar_arrive(tfree_bar);
+      // gate math (fast exp / reciprocal: |error| ~1e-7, far inside the parity budget)
+      float rr[8], zz[8], nn[8], gh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = b_ok && jb + i < H;
+        gh[i] = an[i] + bn[i];
+        rr[i] = __fdividef(1.f, 1.f + __expf(-(gr[i] + ar[i] + br[i])));
+        zz[i] = __fdividef(1.f, 1.f + __expf(-(gz[i] + az[i] + bz[i])));
+        nn[i] = 1.f - __fdividef(2.f, __expf(2.f * (gn[i] + rr[i] * gh[i])) + 1.f);
+        const float h = (1.f - zz[i]) * nn[i] + zz[i] * h_own[i];
+        h_own[i] = ok ? h : 0.f;
+      }
+      if (s + 1 < T) {
+        // publish the operand image of h_s (parity s&1): chunk (jb/8), row `row`; raise this slice's flag as soon as
+        // the image stores of the 8 worker warps are visible (the out / gates stores below are not waited for)
+        uint4 hi, lo;
+        pack8(h_own, hi, lo);
+        unsigned char* img = img0 + (size_t)(s & 1) * 2 * a_half;
+        const int off = ((jb >> 3) * PBM + row) * 16;
+        *reinterpret_cast<uint4*>(img + off) = hi;
+        if (p.x3) *reinterpret_cast<uint4*>(img + a_half + off) = lo;
+        GRU_MARK(5);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 worker warps
+        GRU_MARK(6);
+        if (tid == 0) st_release_u32(flags + slice * 32, (unsigned)(s + 1));  // release: cumulative over bar.sync
+        GRU_MARK(7);
+      }
+      // layer output and saved gates: kept in registers, stored at the next step while its image is in flight
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ph[i] = h_own[i]; pr[i] = rr[i]; pz[i] = zz[i]; pn[i] = nn[i]; pg[i] = gh[i]; }
+      pt = t;
+      if (s == 0 || s + 1 == T) store_prev();  // step 0 has no fetch phase; the last step has no successor
     }
   }
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -499,12 +621,24 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
 
 static inline int kpad_of(int H) { return ((H + HS - 1) / HS) * HS; }
 static inline size_t img_bytes(int H) { return 2 * (size_t)(kpad_of(H) / 8) * PBM * 16; }  // hi + lo
-static inline size_t persist_smem_bytes(int H) { return HDR + (size_t)kpad_of(H) / 8 * (2 * NC + 2 * PBM) * 16; }
+static inline size_t persist_smem_bytes(int H) { return FWD_HDR + (size_t)kpad_of(H) / 8 * (2 * NC + 2 * PBM) * 16; }
 
 }  // namespace grup
 
+int gru_debug_read_timeline(long long* host, int n) {
+  // n <= 1024: step marks; n > 1024: step marks followed by the per-slice table
+  int n1 = n < 64 * 16 ? n : 64 * 16;
+  if (cudaMemcpyFromSymbol(host, grup::g_gru_timeline, sizeof(long long) * n1) != cudaSuccess) return -2;
+  int n2 = n - n1;
+  if (n2 > 64 * 3 * grup::MAX_SLICES) n2 = 64 * 3 * grup::MAX_SLICES;
+  if (n2 > 0 && cudaMemcpyFromSymbol(host + n1, grup::g_gru_slices, sizeof(long long) * n2) != cudaSuccess) return -2;
+  return 0;
+}
+
 // A launch keeps every CTA resident: at most 148 CTAs -> batch chunks of `rows_per_launch` clips.
-bool gru_persist_supported(int H) { return H >= 16 && grup::persist_smem_bytes(H) <= 227 * 1024; }
+bool gru_persist_supported(int H) {
+  return H >= 16 && grup::persist_smem_bytes(H) <= 227 * 1024 && grup::kpad_of(H) / grup::HS <= grup::MAX_SLICES;
+}
 static int gru_persist_tiles_per_launch(int H) {
   const int S = grup::kpad_of(H) / grup::HS;
   int tiles = 148 / (2 * S);
@@ -514,7 +648,7 @@ static int gru_persist_tiles_per_launch(int H) {
 size_t gru_persist_ws_bytes(int B, int H) {
   if (!gru_persist_supported(H) || gru_persist_tiles_per_launch(H) == 0) return 0;
   const int nbt = (B + grup::PBM - 1) / grup::PBM;
-  return (size_t)2 * nbt * 2 * grup::img_bytes(H) + (size_t)2 * nbt * 32 * sizeof(unsigned) + 256;
+  return (size_t)2 * nbt * 2 * grup::img_bytes(H) + (size_t)2 * nbt * grup::MAX_SLICES * 32 * sizeof(unsigned) + 512;
 }
 
 int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const float* bhh_f, long bhh_dstride,
@@ -533,16 +667,17 @@ int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
   base += (256 - (reinterpret_cast<uintptr_t>(base) & 255)) & 255;
   unsigned int* cnt = reinterpret_cast<unsigned int*>(base);
-  unsigned char* xchg = base + (((size_t)2 * nbt_all * 32 * sizeof(unsigned) + 255) & ~(size_t)255);
-  if (cudaMemsetAsync(cnt, 0, (size_t)2 * nbt_all * 32 * sizeof(unsigned), (cudaStream_t)stream) != cudaSuccess)
-    return S2AG_ERR_LAUNCH;
+  const size_t flag_bytes = (size_t)2 * nbt_all * MAX_SLICES * 32 * sizeof(unsigned);  // [group][slice], 128 B apart
+  unsigned char* xchg = base + ((flag_bytes + 255) & ~(size_t)255);
+  if (cudaMemsetAsync(cnt, 0, flag_bytes, (cudaStream_t)stream) != cudaSuccess) return S2AG_ERR_LAUNCH;
   for (int t0 = 0; t0 < nbt_all; t0 += tiles_max) {  // every launch keeps all of its CTAs resident
     const int nbt = nbt_all - t0 < tiles_max ? nbt_all - t0 : tiles_max;
     Params p;
     p.gi = gi; p.whh = whh_f; p.whh_dstride = whh_dstride; p.bhh = bhh_f; p.bhh_dstride = bhh_dstride;
     p.out = out; p.gates = gates; p.xchg = xchg; p.cnt = cnt;
     p.B = B; p.T = T; p.H = H; p.Kpad = kpad_of(H); p.S = S; p.nbt = nbt_all; p.bt0 = t0; p.x3 = x3;
-    S2AG_LAUNCH(kfn, dim3(S, nbt, 2), PTHREADS, persist_smem_bytes(H), stream, p);
+    p.dbg = (umma::g_dbg_flags & 2) ? 1 : 0;
+    S2AG_LAUNCH(kfn, dim3(S, nbt, 2), FWD_THREADS, persist_smem_bytes(H), stream, p);
   }
   return S2AG_OK;
 }

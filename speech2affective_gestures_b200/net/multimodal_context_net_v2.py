@@ -385,15 +385,34 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
         self.do_flatten_parameters = False
         self.flatten_parameters_()
 
-    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None):
+    def encode_shared(self, pre_seq, in_mfcc, repeats=1):
+        """The dropout-free, BatchNorm-only encoders (AffEncoder on the seed poses, MFCCEncoder): within one GAN
+        iteration the reference evaluates them on the SAME inputs with the SAME weights in each of its generator
+        passes (processor_v2.py:798, 823, 909), so they are computed once and handed to every pass through
+        `forward(..., shared=...)`; `repeats` = number of passes they stand for (BatchNorm running statistics are
+        advanced as that many identical updates, see ops.bn_repeat)."""
+        with ops.bn_repeat(repeats):
+            p = self.aff_encoder(pre_seq[..., :-1])
+            a = self.audio_encoder(in_mfcc) if self.input_context in ('both', 'audio') else None
+        return p, a
+
+    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None, shared=None):
         B, T = pre_seq.shape[0], pre_seq.shape[1]
         buf = torch.empty(B, T, self.in_size, dtype=torch.float32, device=pre_seq.device)
         pieces, slices = [], []
         col = 0
-        p = self.aff_encoder(pre_seq[..., :-1], out=ops.col_slice(buf, col, col + 8))
+        if shared is None:
+            p = self.aff_encoder(pre_seq[..., :-1], out=ops.col_slice(buf, col, col + 8))
+        else:
+            p = shared[0]
+            buf[:, :, col:col + 8].copy_(p.detach())
         pieces.append(p); slices.append((col, col + 8)); col += 8
         if self.input_context in ('both', 'audio'):
-            a = self.audio_encoder(in_mfcc, out=ops.col_slice(buf, col, col + 32))
+            if shared is None:
+                a = self.audio_encoder(in_mfcc, out=ops.col_slice(buf, col, col + 32))
+            else:
+                a = shared[1]
+                buf[:, :, col:col + 32].copy_(a.detach())
             pieces.append(a); slices.append((col, col + 32)); col += 32
         if self.input_context in ('both', 'text'):
             t, _ = self.text_encoder(in_text, out=ops.col_slice(buf, col, col + 32))

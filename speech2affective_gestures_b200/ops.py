@@ -211,16 +211,39 @@ class _BnState:
     __slots__ = ("x", "ldx", "M", "C", "mean", "invstd", "training", "act", "slope", "y", "ldy", "cmap", "pmap")
 
 
+_bn_repeat = [1]
+
+
+class bn_repeat:
+    """Context: a train-mode BatchNorm forward inside it stands for `n` identical forward calls of the
+    reference (same input, same weights => same batch statistics and output); the running statistics are
+    updated as n successive momentum updates would, r <- (1-m)^n r + (1-(1-m)^n) s, and
+    num_batches_tracked advances by n.  Used where the reference runs the SAME encoder on the SAME input
+    several times per step (processor_v2.py:798,823,909: three generator passes)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        self.prev = _bn_repeat[0]
+        _bn_repeat[0] = self.n
+
+    def __exit__(self, *a):
+        _bn_repeat[0] = self.prev
+
+
 def _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2=None, ldadd=0, cmap=None, pmap=None):
     """x2/y2: row views. bn: module-like with weight,bias,running_mean,running_var,momentum,eps."""
     mean = _empty((C,), x2)
     invstd = _empty((C,), x2)
     ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    rep = _bn_repeat[0] if training else 1
+    momentum = float(bn.momentum) if rep == 1 else 1.0 - (1.0 - float(bn.momentum)) ** rep
     _C.call("s2ag_bn_fwd", _p(x2), ldx, M, C, _p(bn.weight), _p(bn.bias), _p(pmap), _p(bn.running_mean),
-            _p(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps), _p(add2), ldadd, _p(y2), ldy,
+            _p(bn.running_var), 1 if training else 0, momentum, float(bn.eps), _p(add2), ldadd, _p(y2), ldy,
             _p(cmap), act, float(slope), _p(mean), _p(invstd), _p(ws), _stream(x2))
     if training:
-        bn._s2ag_batches = getattr(bn, "_s2ag_batches", 0) + 1
+        bn._s2ag_batches = getattr(bn, "_s2ag_batches", 0) + rep
     s = _BnState()
     s.x, s.ldx, s.M, s.C, s.mean, s.invstd, s.training = x2, ldx, M, C, mean, invstd, training
     s.act, s.slope, s.y, s.ldy, s.cmap, s.pmap = act, float(slope), y2, ldy, cmap, pmap

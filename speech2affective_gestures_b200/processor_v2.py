@@ -175,13 +175,20 @@ class Processor(object):
         pre_seq = self.make_pre_seq(target_poses)
         if train:
             ops.advance_seed_nonce(self.device)
+        use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
+        # AffEncoder(pre_seq) and MFCCEncoder(in_mfcc) have no dropout and G's weights do not change between the
+        # generator passes of one iteration (:798, :823, :909): evaluate them once for all passes.
+        n_passes = (1 if gan_on else 0) + 1 + (1 if use_div else 0)
+        with torch.set_grad_enabled(train):
+            shared = G.encode_shared(pre_seq, in_mfcc, repeats=n_passes if G.training else 1)
+        shared_ng = tuple(None if t is None else t.detach() for t in shared)
 
         # ---- train D (processor_v2.py:791-814)
         if gan_on:
             if train:
                 D.zero_grad()
             with torch.no_grad():  # the reference builds and discards this graph; only .detach() is used (:809)
-                out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices)
+                out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared_ng)
             with torch.set_grad_enabled(train):
                 dis_real = D(target_poses, in_text)
                 dis_fake = D(out_for_d, in_text)
@@ -198,7 +205,7 @@ class Processor(object):
         with torch.no_grad():
             out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices)
         with torch.set_grad_enabled(train):
-            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices)
+            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared)
             # D's own parameter gradients from this pass are discarded by the reference (zero_grad at the
             # next D step, :794), so they are not computed; gradients still flow through D into G.
             d_params = [p for p in D.parameters() if p.requires_grad]
@@ -210,7 +217,6 @@ class Processor(object):
                 for p in d_params:
                     p.requires_grad_(True)
         out_rand = z_rand = None
-        use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
         if use_div:
             if cfg.z_type == 'speaker':
                 # torch.randperm(B) of processor_v2.py:903; drawn as argsort(uniform) on the device so that
@@ -221,7 +227,7 @@ class Processor(object):
             else:
                 rand_vids = None
             with torch.no_grad():  # only used detached (:913, :919)
-                out_rand, z_rand, _, _ = G(pre_seq, in_text, in_mfcc, rand_vids)
+                out_rand, z_rand, _, _ = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng)
         use_kld = use_div and cfg.z_type == 'speaker'
         weights = (cfg.loss_regression_weight, cfg.loss_kld_weight if use_kld else 0.0,
                    cfg.loss_reg_weight if use_div else 0.0, cfg.loss_gan_weight if gan_on else 0.0)
