@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
   const uint32_t ncols = Kpad <= 32 ? 32u : Kpad <= 64 ? 64u : Kpad <= 128 ? 128u : Kpad <= 256 ? 256u : 512u;
 
   if (tid == 0) {
-    mbar_init(mma_bar, 1);
+    mbar_init(mma_bar, Kpad <= 256 ? 1 : 2);  // one arrival per MMA-issuer thread (one per accumulator half)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(sbase + 8, ncols);
@@ -466,44 +466,54 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
   // N split: one MMA covers at most 256 accumulator columns
   const int n1 = Kpad <= 256 ? Kpad : 160, n2 = Kpad - n1;
 
-  for (int step = 0; step < T; ++step) {
-    const int fs = T - 1 - step;                         // forward step index being differentiated
+  // per-step operands (dout, h_prev, saved gates): loaded one step ahead, they do not depend on the recurrence
+  float ndh[8], nhp[8], nr[8], nz[8], nn_[8], nghn[8];
+  auto load_step = [&](int step) {
+    const int fs = T - 1 - step;
     const int t = dir == 0 ? fs : T - 1 - fs;
     const int tprev = dir == 0 ? t - 1 : t + 1;
     const long rowi = (long)(b_ok ? b : 0) * T + t;
-    float dh[8], hp[8], r[8], z[8], n[8], ghn[8];
-    {
-      const float* dp = p.dout + rowi * p.lddout + (long)dir * p.dir_stride + jb;
-      const float* hq = p.out + ((long)(b_ok ? b : 0) * T + (fs > 0 ? tprev : t)) * 2 * H + (long)dir * H + jb;
-      if (vec_ok && b_ok) {
-        const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp) + 1);
-        dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
-        if (fs > 0) {
-          const float4 h0 = __ldg(reinterpret_cast<const float4*>(hq)), h1 = __ldg(reinterpret_cast<const float4*>(hq) + 1);
-          hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w; hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) hp[i] = 0.f;
-        }
+    const float* dp = p.dout + rowi * p.lddout + (long)dir * p.dir_stride + jb;
+    const float* hq = p.out + ((long)(b_ok ? b : 0) * T + (fs > 0 ? tprev : t)) * 2 * H + (long)dir * H + jb;
+    if (vec_ok && b_ok) {
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+      ndh[0] = d0.x; ndh[1] = d0.y; ndh[2] = d0.z; ndh[3] = d0.w; ndh[4] = d1.x; ndh[5] = d1.y; ndh[6] = d1.z; ndh[7] = d1.w;
+      if (fs > 0) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(hq)), h1 = __ldg(reinterpret_cast<const float4*>(hq) + 1);
+        nhp[0] = h0.x; nhp[1] = h0.y; nhp[2] = h0.z; nhp[3] = h0.w; nhp[4] = h1.x; nhp[5] = h1.y; nhp[6] = h1.z; nhp[7] = h1.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = b_ok && jb + i < H;
-          dh[i] = ok ? __ldg(dp + i) : 0.f;
-          hp[i] = (ok && fs > 0) ? __ldg(hq + i) : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) nhp[i] = 0.f;
       }
-      const float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + jb) * B + (b_ok ? b : 0);
-      const long gstride = (long)H * B;
+    } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool ok = b_ok && jb + i < H;
-        r[i] = ok ? __ldg(gs + (long)i * B) : 0.f;
-        z[i] = ok ? __ldg(gs + gstride + (long)i * B) : 0.f;
-        n[i] = ok ? __ldg(gs + 2 * gstride + (long)i * B) : 0.f;
-        ghn[i] = ok ? __ldg(gs + 3 * gstride + (long)i * B) : 0.f;
+        ndh[i] = ok ? __ldg(dp + i) : 0.f;
+        nhp[i] = (ok && fs > 0) ? __ldg(hq + i) : 0.f;
       }
     }
+    const float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + jb) * B + (b_ok ? b : 0);
+    const long gstride = (long)H * B;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = b_ok && jb + i < H;
+      nr[i] = ok ? __ldg(gs + (long)i * B) : 0.f;
+      nz[i] = ok ? __ldg(gs + gstride + (long)i * B) : 0.f;
+      nn_[i] = ok ? __ldg(gs + 2 * gstride + (long)i * B) : 0.f;
+      nghn[i] = ok ? __ldg(gs + 3 * gstride + (long)i * B) : 0.f;
+    }
+  };
+  load_step(0);
+
+  for (int step = 0; step < T; ++step) {
+    const int fs = T - 1 - step;                         // forward step index being differentiated
+    const int t = dir == 0 ? fs : T - 1 - fs;
+    const long rowi = (long)(b_ok ? b : 0) * T + t;
+    float dh[8], hp[8], r[8], z[8], n[8], ghn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dh[i] = ndh[i]; hp[i] = nhp[i]; r[i] = nr[i]; z[i] = nz[i]; n[i] = nn_[i]; ghn[i] = nghn[i]; }
+    if (step + 1 < T) load_step(step + 1);
     float dr[8], dz[8], dn[8], dnr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -514,7 +524,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       dnr[i] = dn[i] * r[i];
       carry[i] = dh[i] * z[i];
     }
-    if (b_ok) {  // dgi / dgh rows for the time-batched weight-gradient GEMMs
+    auto store_grads = [&]() {  // dgi / dgh rows for the time-batched weight-gradient GEMMs
+      if (!b_ok) return;
       float* a = p.dgi + (rowi * 2 + dir) * 3 * H + jb;
       float* c = p.dgh + (rowi * 2 + dir) * 3 * H + jb;
       if (vec_ok) {
@@ -537,7 +548,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
           }
         }
       }
-    }
+    };
+    if (fs == 0) store_grads();
     if (fs > 0) {
       // A operand = this CTA's dgh tile [128 x 48]: local gate row c = g*16 + u0 + i  ->  chunk g*2 + wg
       {
@@ -554,30 +566,28 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       }
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if ((tid == 0) || (tid == 32 && n2 > 0)) {
+        // one issuer thread per accumulator half: 9 dependent tcgen05.mma each instead of 18 in one stream
         tc_fence_after();
+        const int half = tid == 0 ? 0 : 1;
         const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
         const uint32_t a_lbo = PBM * 16, w_lbo = (uint32_t)Kpad * 16;
+        const int nn = half == 0 ? n1 : n2;
+        const uint32_t idesc = make_idesc(nn);
+        const uint32_t d_tmem = tmem_base + (half == 0 ? 0u : (uint32_t)n1);
+        const uint32_t w_off = half == 0 ? 0u : (uint32_t)n1 * 16u;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int nn = half == 0 ? n1 : n2;
-          if (nn == 0) continue;
-          const uint32_t idesc = make_idesc(nn);
-          const uint32_t d_tmem = tmem_base + (half == 0 ? 0u : (uint32_t)n1);
-          const uint32_t w_off = half == 0 ? 0u : (uint32_t)n1 * 16u;
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            const uint32_t ah = sa + kk * 2 * a_lbo, al = ah + a_half;
-            const uint32_t wh = sw + kk * 2 * w_lbo + w_off, wl = wh + w_half;
-            const uint64_t dah = make_desc(ah, a_lbo, 128), dwh = make_desc(wh, w_lbo, 128);
-            uint32_t acc = kk > 0 ? 1u : 0u;
-            if (p.x3) {
-              mma_bf16(d_tmem, make_desc(al, a_lbo, 128), dwh, idesc, acc);
-              mma_bf16(d_tmem, dah, make_desc(wl, w_lbo, 128), idesc, 1u);
-              acc = 1u;
-            }
-            mma_bf16(d_tmem, dah, dwh, idesc, acc);
+        for (int kk = 0; kk < 3; ++kk) {
+          const uint32_t ah = sa + kk * 2 * a_lbo, al = ah + a_half;
+          const uint32_t wh = sw + kk * 2 * w_lbo + w_off, wl = wh + w_half;
+          const uint64_t dah = make_desc(ah, a_lbo, 128), dwh = make_desc(wh, w_lbo, 128);
+          uint32_t acc = kk > 0 ? 1u : 0u;
+          if (p.x3) {
+            mma_bf16(d_tmem, make_desc(al, a_lbo, 128), dwh, idesc, acc);
+            mma_bf16(d_tmem, dah, make_desc(wl, w_lbo, 128), idesc, 1u);
+            acc = 1u;
           }
+          mma_bf16(d_tmem, dah, dwh, idesc, acc);
         }
         mma_commit(mma_bar);
       }
@@ -595,14 +605,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
-        __threadfence();
-        atomicAdd(const_cast<unsigned*>(cnt), 1u);
+        // arrive (release: cumulative over the __syncthreads above) and wait for the other slices of the group
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+      }
+      store_grads();  // off the critical path: overlaps the wait for the other CTAs
+      if (tid == 0) {
         const unsigned target = (unsigned)S * (unsigned)(step + 1);
         unsigned spins = 0;
-        while (ld_acquire_u32(cnt) < target) {
+        while (*reinterpret_cast<const volatile unsigned*>(cnt) < target) {
           if (++spins > (1u << 26)) __trap();
         }
-        __threadfence();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
       }
       __syncthreads();
       // carry[b, j] += sum over slices of their partial columns j (this thread: 8 columns, its clip)
