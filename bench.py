@@ -303,7 +303,16 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: the captured graph holds NCCL work; destroying the communicator underneath it can block
+        # (observed on 2 GPUs).  Drop the graph, drain the device, rendezvous once more and leave without the
+        # communicator destructor.
+        pr._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

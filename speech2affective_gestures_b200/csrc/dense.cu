@@ -186,9 +186,11 @@ extern "C" int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, 
   S2AG_CHECK_ARG(sh > 0 && sw > 0 && dh > 0 && dw > 0 && ldpix_x >= Cin && ldpix_y >= Cout);
   int Ho = conv_out(H, KH, sh, ph, dh), Wo = conv_out(W, KW, sw, pw, dw);
   S2AG_CHECK_ARG(Ho > 0 && Wo > 0);
-  LdConv<ORDER_CKK> a{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dw, +1, -ph, -pw, ldpix_x};
+  // k order (kh, kw, c): the activation operand gathers contiguous channels of one pixel (16-byte loads when
+  // Cin % 4 == 0); the weight operand reads the reference layout [Cout][Cin][KH][KW] through LdWkkc.
+  LdConv<ORDER_KKC> a{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dw, +1, -ph, -pw, ldpix_x};
   int K = Cin * KH * KW;
-  LdPlain<true> b{w, (long)K, 1, 0};
+  LdWkkc b{w, Cin, KH * KW};
   launch_gemm(a, b, make_epi(y, ldpix_y, bias, act, slope, 0), N * Ho * Wo, Cout, K, 1, 1, stream);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
@@ -201,9 +203,10 @@ extern "C" int s2ag_conv_bwd_data(const float* dy, long ldpix_dy, int N, int H, 
   int Ho = conv_out(H, KH, 1, ph, dh), Wo = conv_out(W, KW, 1, pw, dw);
   S2AG_CHECK_ARG(Ho > 0 && Wo > 0 && ldpix_dy >= Cout && ldpix_dx >= Cin);
   // dx[n,hi,wi,c] = sum_{co,kh,kw} dy[n, hi+ph-kh*dh, wi+pw-kw*dw, co] * w[co,c,kh,kw]
-  LdConv<ORDER_CKK> a{dy, Ho, Wo, Cout, H, W, KH, KW, 1, 1, dh, dw, -1, ph, pw, ldpix_dy};
+  // contraction index (kh, kw, co): contiguous output channels of one dy pixel
+  LdConv<ORDER_KKC> a{dy, Ho, Wo, Cout, H, W, KH, KW, 1, 1, dh, dw, -1, ph, pw, ldpix_dy};
   int KK = KH * KW;
-  LdWdgrad<ORDER_CKK> b{w, Cout, KK, (long)Cin * KK, (long)KK, 1};
+  LdWdgrad<ORDER_KKC> b{w, Cout, KK, (long)Cin * KK, (long)KK, 1};
   launch_gemm(a, b, make_epi(dx, ldpix_dx, nullptr, 0, 0.f, accumulate ? 1 : 0), N * H * W, Cin, Cout * KK, 1, 1,
               stream);
   S2AG_CHECK_LAUNCH();
@@ -221,9 +224,13 @@ extern "C" int s2ag_conv_bwd_weight(const float* dy, long ldpix_dy, const float*
   int K = Cin * KH * KW;
   // dw[co, kcol] += sum_row dy[row, co] * im2col(x)[row, kcol]
   LdPlain<false> a{dy, 1, ldpix_dy, 0};
-  LdT<LdConv<ORDER_CKK>> b{LdConv<ORDER_CKK>{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dwd, +1, -ph, -pw, ldpix_x}};
+  // columns in (kh, kw, c) order (consecutive columns = contiguous channels of x); the epilogue stores column
+  // tap*Cin + c at the reference position c*KH*KW + tap of dw[co]
+  LdT<LdConv<ORDER_KKC>> b{LdConv<ORDER_KKC>{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dwd, +1, -ph, -pw, ldpix_x}};
   int sk = pick_splitk(Cout, K, Mrows, 1);
-  launch_gemm(a, b, make_epi(dw, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), Cout, K, Mrows, 1, sk, stream);
+  EpiGeneric e = make_epi(dw, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1);
+  e.perm_C = Cin; e.perm_KK = KH * KW;
+  launch_gemm(a, b, e, Cout, K, Mrows, 1, sk, stream);
   if (db) launch_colsum(dy, ldpix_dy, db, Mrows, Cout, stream);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;

@@ -227,6 +227,37 @@ struct LdWdgrad {
   }
 };
 
+// Convolution weight in the reference layout w[Cout][Cin][KK] read with the k order (tap, c) of LdConv<ORDER_KKC>:
+// element(row = co, k = tap*Cin + c) = w[(co*Cin + c)*KK + tap].  (The activation operand then gathers contiguous
+// channels; the weight tensor is small and cache-resident, its strided reads are cheap.)
+struct LdWkkc {
+  static constexpr bool kContig = true;
+  const float* w; int Cin, KK;
+  __device__ __forceinline__ float operator()(int, int row, int k) const {
+    const int c = k % Cin, tap = k / Cin;
+    return __ldg(w + ((long)row * Cin + c) * KK + tap);
+  }
+  struct Cur { const float* wr; int k, c, tap; };
+  __device__ __forceinline__ Cur cursor(int, int row, int k) const {
+    return Cur{w + (long)row * Cin * KK, k, k % Cin, k / Cin};
+  }
+  template <bool FULL>
+  __device__ __forceinline__ void load8_impl(const Cur& cu, int kend, float (&v)[8]) const {
+    int c = cu.c, tap = cu.tap;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = (FULL || cu.k + i < kend) ? __ldg(cu.wr + (long)c * KK + tap) : 0.f;
+      if (++c == Cin) { c = 0; ++tap; }
+    }
+  }
+  __device__ __forceinline__ void load8(const Cur& cu, int kend, float (&v)[8]) const { load8_impl<false>(cu, kend, v); }
+  __device__ __forceinline__ void load8_full(const Cur& cu, float (&v)[8]) const { load8_impl<true>(cu, 0, v); }
+  __device__ __forceinline__ void advance(Cur& cu) const {
+    cu.k += LD_STEP; cu.c += LD_STEP;
+    while (cu.c >= Cin) { cu.c -= Cin; ++cu.tap; }
+  }
+};
+
 // ---------------------------------------------------------------- epilogues
 // v = alpha*acc (+bias[n]) ; v = act(v) ; v *= act'(mul_src[m,n]) ; store / add / atomicAdd
 struct EpiGeneric {
@@ -236,12 +267,14 @@ struct EpiGeneric {
   int act; float slope;
   int mode;  // 0 store, 1 C += v, 2 atomicAdd
   const float* mul_src; long ld_mul; int mul_act; float mul_slope;
+  int perm_C, perm_KK;  // perm_C > 0: output column n = tap*perm_C + c is stored at column c*perm_KK + tap
   __device__ __forceinline__ void operator()(int b, int m, int n, float acc, bool partial) const {
     float v = alpha * acc;
     if (bias) v += __ldg(bias + b * bias_bstride + n);
     v = s2ag_act(v, act, slope);
     if (mul_src) v *= s2ag_act_grad_from_out(__ldg(mul_src + (long)m * ld_mul + n), mul_act, mul_slope);
-    float* dst = C + b * bstride + (long)m * ldc + n;
+    const int ncol = perm_C > 0 ? (n % perm_C) * perm_KK + n / perm_C : n;
+    float* dst = C + b * bstride + (long)m * ldc + ncol;
     if (partial || mode == 2) atomicAdd(dst, v);
     else if (mode == 1) *dst += v;
     else *dst = v;
@@ -251,6 +284,7 @@ static inline EpiGeneric make_epi(float* C, long ldc, const float* bias = nullpt
                                   int mode = 0) {
   EpiGeneric e; e.C = C; e.ldc = ldc; e.bstride = 0; e.bias = bias; e.bias_bstride = 0; e.alpha = 1.f;
   e.act = act; e.slope = slope; e.mode = mode; e.mul_src = nullptr; e.ld_mul = 0; e.mul_act = 0; e.mul_slope = 0.f;
+  e.perm_C = 0; e.perm_KK = 0;
   return e;
 }
 
