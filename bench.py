@@ -93,6 +93,47 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+
+# ncu --set full capture of the roofline launch (profiles/r01_ncu_umma_gemm.txt): dram__bytes_read.sum + dram__bytes_write.sum
+ROOFLINE_TRAFFIC_BYTES = None
+
+
+def roofline(B, dev, lib, clips_per_s_per_gpu=None):
+    """The dense-contraction engine (gemm_umma_kernel, tcgen05) carries ~45 % of the step's device time; its largest
+    single shape is the GRU layer input projection [B*34, 600] x [600, 2*900] (both directions).  achieved =
+    algorithmic 2*M*N*K / CUDA-event time of that launch; the kernel issues 3 bf16 MMAs per algorithmic MAC in the
+    fp32-grade bf16x3 mode, so its tensor-pipe ceiling is 1/3 of the bf16 peak it is reported against."""
+    import torch
+    from speech2affective_gestures_b200 import _C, ops
+    pk = peaks()
+    M, N, K = B * 34, 1800, 600
+    x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; y = torch.empty(M, N, device=dev)
+    bias = torch.zeros(N, device=dev)
+    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+    st = ops._stream(x)
+    call = lambda: _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(bias), ops._p(y), N, M, N, K, 0, 0.0, st)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    reps, tot = 10, 0.0
+    for _ in range(reps):
+        flush.zero_()  # L2 flush between timed launches
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(); call(); k1.record()
+        torch.cuda.synchronize()
+        tot += k0.elapsed_time(k1)
+    kms = tot / reps
+    ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
+    r = {"bound": "tensor", "kernel": "gemm_umma_kernel<LdPlain,LdPlain,EpiGeneric> (tcgen05; GRU input projection "
+                                      "%dx%dx%d, fp32 operands split bf16 hi/lo on the fly)" % (M, N, K),
+         "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
+         "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": pk["source"] + " (MEASURED_PEAKS.json bf16_tflops, burst)",
+         "kernel_ms": kms, "algorithmic_flops": 2.0 * M * N * K,
+         "l2": "160 MB buffer zeroed between timed launches"}
+    if clips_per_s_per_gpu is not None:
+        r["step_frac_of_tensor_roofline"] = clips_per_s_per_gpu * FLOP_PER_CLIP / 1e12 / pk["bf16_sustained"]
+    return r
+
 # ----------------------------------------------------------------------------- clocks sampler
 class Clocks:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -145,6 +186,9 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16x1"],
+                    help="tensor-core operand precision: bf16x3 = fp32-grade (parity configuration, default), bf16x1 = BASELINE config 3")
+    ap.add_argument("--roofline-only", action="store_true", help="run only the roofline kernel (for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -165,6 +209,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _C.lib()
     assert lib.s2ag_is_device_build() == 1, "CUDA extension missing: there is no fallback"
+    assert lib.s2ag_set_precision(0 if args.precision == "bf16x3" else 1) == 0
+    if args.roofline_only:
+        print(json.dumps({"roofline": roofline(args.batch_per_gpu, dev, lib)}))
+        return
 
     cfg, O = cfg_namespace()
     B = args.batch_per_gpu
@@ -249,31 +297,8 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (t_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel, timed alone with CUDA events on its launch stream
-    roof = None
-    if rank == 0:
-        pk = peaks()
-        M, N, K = B * 34, 1800, 600  # GRU layer input projection, both directions (gemm_simt_kernel)
-        x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev); y = torch.empty(M, N, device=dev)
-        bias = torch.zeros(N, device=dev)
-        st = ops._stream(x)
-        call = lambda: _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(bias), ops._p(y), N, M, N, K, 0, 0.0, st)
-        for _ in range(3):
-            call()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        reps = 10
-        k0.record()
-        for _ in range(reps):
-            call()
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_simt_kernel (GRU input projection %dx%dx%d, fp32 SIMT)" % (M, N, K),
-                "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
-                "traffic": None, "peak_source": pk["source"], "kernel_ms": kms,
-                "step_frac_of_tensor_roofline": (value / world) * FLOP_PER_CLIP / 1e12 / pk["bf16_sustained"]}
+    # ---- roofline of the dominant kernel family, timed alone with CUDA events on its launch stream
+    roof = roofline(B, dev, lib, value / world) if rank == 0 else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -288,11 +313,13 @@ def main():
             "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step", "value": value,
             "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.precision == "bf16x3" else "bf16", "data": "synthetic",
             "config": {"workload": "full GAN step (D step + G step: 3 G fwd, 1 frozen tri-modal fwd incl. WavEncoder, "
                                    "3 D fwd, G+D bwd, 2 Adam), %d clips/GPU, 34 frames x 27-D, audio %d samples, "
                                    "10-token text, n_words=%d, dropout as shipped" % (B, AUDIO_LEN, N_WORDS),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "precision": "%s (fp32 storage and accumulation; tensor-core operands %s)" % (
+                           args.precision, "split bf16 hi+lo, 3 MMAs" if args.precision == "bf16x3" else "single bf16"),
                        "l2": "per-step working set (activations+saved gates+params, >1 GB) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": use_graph},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,

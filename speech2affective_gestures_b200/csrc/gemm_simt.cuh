@@ -33,12 +33,25 @@ struct LdPlain {
   __device__ __forceinline__ float operator()(int b, int row, int k) const {
     return __ldg(p + b * bstride + (long)row * ld_row + (long)k * ld_k);
   }
-  struct Cur { const float* q; int k; bool vec; };
+  struct Cur { const float* q; int k; int vec; };  // vec: 2 = one 32-byte load, 1 = two 16-byte loads, 0 = scalar
   __device__ __forceinline__ Cur cursor(int b, int row, int k) const {
     const float* q = p + b * bstride + (long)row * ld_row + (long)k * ld_k;
-    return Cur{q, k, KCONTIG && ld_k == 1 && s2ag_aligned16(q)};  // advance() keeps the 16-byte alignment
+    int vec = 0;
+    if (KCONTIG && ld_k == 1) {
+      const unsigned long long a = reinterpret_cast<unsigned long long>(q);
+      vec = (a & 31ull) == 0 ? 2 : ((a & 15ull) == 0 ? 1 : 0);  // advance() (+128 bytes) keeps the alignment
+    }
+    return Cur{q, k, vec};
   }
   __device__ __forceinline__ void load8_full(const Cur& c, float (&v)[8]) const {  // all 8 k in range
+#ifndef S2AG_EMU
+    if (c.vec == 2) {  // one full 32-byte sector per lane (LDG.E.256)
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                   : "l"(c.q));
+      return;
+    }
+#endif
     if (c.vec) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(c.q)), b = __ldg(reinterpret_cast<const float4*>(c.q) + 1);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
