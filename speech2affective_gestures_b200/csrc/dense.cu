@@ -6,6 +6,15 @@
 
 using namespace s2ag;
 
+#ifndef S2AG_EMU
+namespace s2ag {
+// umma_conv.cu: stride-1 convolutions as shifted-window tcgen05 contractions (weights stationary in shared memory)
+bool conv_shift_launch(const float* x, long ldpix_x, int N, int H, int W, int Cin, const float* w, int w_mode, int w_ci,
+                       const float* bias, float* y, long ldpix_y, int Cout, int KH, int KW, int ph, int pw, int Ho,
+                       int Wo, int act, float slope, int accumulate, void* stream);
+}
+#endif
+
 // ------------------------------------------------------------------ column sums (bias grads)
 // db[n] += sum_m dy[m*ld + n]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long ld, float* __restrict__ db,
@@ -186,6 +195,14 @@ extern "C" int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, 
   S2AG_CHECK_ARG(sh > 0 && sw > 0 && dh > 0 && dw > 0 && ldpix_x >= Cin && ldpix_y >= Cout);
   int Ho = conv_out(H, KH, sh, ph, dh), Wo = conv_out(W, KW, sw, pw, dw);
   S2AG_CHECK_ARG(Ho > 0 && Wo > 0);
+#ifndef S2AG_EMU
+  if (g_engine == 0 && sh == 1 && sw == 1 && dh == 1 && dw == 1 &&
+      conv_shift_launch(x, ldpix_x, N, H, W, Cin, w, 0, Cin, bias, y, ldpix_y, Cout, KH, KW, ph, pw, Ho, Wo, act, slope, 0,
+                        stream)) {
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
+#endif
   // k order (kh, kw, c): the activation operand gathers contiguous channels of one pixel (16-byte loads when
   // Cin % 4 == 0); the weight operand reads the reference layout [Cout][Cin][KH][KW] through LdWkkc.
   LdConv<ORDER_KKC> a{x, H, W, Cin, Ho, Wo, KH, KW, sh, sw, dh, dw, +1, -ph, -pw, ldpix_x};
@@ -203,6 +220,14 @@ extern "C" int s2ag_conv_bwd_data(const float* dy, long ldpix_dy, int N, int H, 
   int Ho = conv_out(H, KH, 1, ph, dh), Wo = conv_out(W, KW, 1, pw, dw);
   S2AG_CHECK_ARG(Ho > 0 && Wo > 0 && ldpix_dy >= Cout && ldpix_dx >= Cin);
   // dx[n,hi,wi,c] = sum_{co,kh,kw} dy[n, hi+ph-kh*dh, wi+pw-kw*dw, co] * w[co,c,kh,kw]
+#ifndef S2AG_EMU
+  if (g_engine == 0 && dh == 1 && dw == 1 && KH - 1 - ph >= 0 && KW - 1 - pw >= 0 &&
+      conv_shift_launch(dy, ldpix_dy, N, Ho, Wo, Cout, w, 1, Cin, nullptr, dx, ldpix_dx, Cin, KH, KW, KH - 1 - ph,
+                        KW - 1 - pw, H, W, S2AG_ACT_NONE, 0.f, accumulate, stream)) {
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
+#endif
   // contraction index (kh, kw, co): contiguous output channels of one dy pixel
   LdConv<ORDER_KKC> a{dy, Ho, Wo, Cout, H, W, KH, KW, 1, 1, dh, dw, -1, ph, pw, ldpix_dy};
   int KK = KH * KW;
