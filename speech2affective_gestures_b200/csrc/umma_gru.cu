@@ -66,6 +66,18 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&r)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
+// 32-byte (one full sector) global accesses: 8 consecutive floats, address 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_cg_v8(const float* p, float (&v)[8]) {  // L1 bypassed (data written by other SMs)
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -399,6 +411,7 @@ struct BwdParams {
   float* part;              // [group][parity][S][Kpad][128]
   unsigned int* cnt;
   int B, T, H, Kpad, S, nbt, bt0, x3;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams p) {
@@ -454,6 +467,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
   const bool vec_ok = (H & 3) == 0 && jb + 8 <= H && (p.lddout & 3) == 0 && ((p.dir_stride & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.dout) | reinterpret_cast<uintptr_t>(p.out) |
                         reinterpret_cast<uintptr_t>(p.dgi) | reinterpret_cast<uintptr_t>(p.dgh)) & 15) == 0;
+  // 32-byte stores of the dgi / dgh rows: every gate segment (3H*4, H*4, jb*4 bytes) must keep 32-byte alignment
+  const bool vec32_ok = vec_ok && (H & 7) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.dgi) | reinterpret_cast<uintptr_t>(p.dgh)) & 31) == 0;
   float carry[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) carry[i] = 0.f;
@@ -505,8 +521,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
     }
   };
   load_step(0);
+  const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+#define BWD_MARK(slot) do { if (dbg) g_gru_timeline[(step & 63) * 16 + (slot)] = clock64(); } while (0)
 
   for (int step = 0; step < T; ++step) {
+    BWD_MARK(0);
     const int fs = T - 1 - step;                         // forward step index being differentiated
     const int t = dir == 0 ? fs : T - 1 - fs;
     const long rowi = (long)(b_ok ? b : 0) * T + t;
@@ -528,7 +547,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       if (!b_ok) return;
       float* a = p.dgi + (rowi * 2 + dir) * 3 * H + jb;
       float* c = p.dgh + (rowi * 2 + dir) * 3 * H + jb;
-      if (vec_ok) {
+      if (vec32_ok) {
+        st_global_v8(a, dr); st_global_v8(c, dr);
+        st_global_v8(a + H, dz); st_global_v8(c + H, dz);
+        st_global_v8(a + 2 * H, dn); st_global_v8(c + 2 * H, dnr);
+      } else if (vec_ok) {
         float4* a4; float4* c4;
         a4 = reinterpret_cast<float4*>(a); c4 = reinterpret_cast<float4*>(c);
         a4[0] = make_float4(dr[0], dr[1], dr[2], dr[3]); a4[1] = make_float4(dr[4], dr[5], dr[6], dr[7]);
@@ -565,7 +588,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
         *reinterpret_cast<uint4*>(a_lo + ((2 * 2 + wg) * PBM + row) * 16) = lo;
       }
       fence_async_smem();
+      BWD_MARK(1);
       __syncthreads();
+      BWD_MARK(2);
       if ((tid == 0) || (tid == 32 && n2 > 0)) {
         // one issuer thread per accumulator half: 9 dependent tcgen05.mma each instead of 18 in one stream
         tc_fence_after();
@@ -592,6 +617,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
         mma_commit(mma_bar);
       }
       mbar_wait(mma_bar, (uint32_t)(step & 1));
+      BWD_MARK(3);
       tc_fence_after();
       // accumulator -> partial[parity][slice][k][b]; warpgroup wg takes the k-columns [wg*Kpad/2, +Kpad/2)
       float* mypart = part0 + ((size_t)(step & 1) * S + slice) * part_slice;
@@ -599,16 +625,19 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       for (int c0 = wg * kh; c0 < (wg + 1) * kh; c0 += 8) {
         float v[8];
         tmem_ld8(t_lane + (uint32_t)c0, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mypart[(size_t)(c0 + i) * PBM + row] = v[i];
+        st_global_v8(mypart + (size_t)row * Kpad + c0, v);  // partial[slice][b][k]: one 32-byte sector per store
       }
       tc_fence_before();
+      BWD_MARK(4);
       __syncthreads();
+      BWD_MARK(5);
       if (tid == 0) {
         // arrive (release: cumulative over the __syncthreads above) and wait for the other slices of the group
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
       }
+      BWD_MARK(6);
       store_grads();  // off the critical path: overlaps the wait for the other CTAs
+      BWD_MARK(7);
       if (tid == 0) {
         const unsigned target = (unsigned)S * (unsigned)(step + 1);
         unsigned spins = 0;
@@ -617,14 +646,18 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
         }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
       }
+      BWD_MARK(8);
       __syncthreads();
+      BWD_MARK(9);
       // carry[b, j] += sum over slices of their partial columns j (this thread: 8 columns, its clip)
-      const float* pp = part0 + (size_t)(step & 1) * S * part_slice + (size_t)jb * PBM + row;
+      const float* pp = part0 + (size_t)(step & 1) * S * part_slice + (size_t)row * Kpad + jb;
       for (int sl = 0; sl < S; ++sl) {
-        const float* q = pp + (size_t)sl * part_slice;
+        float v[8];
+        ld_global_cg_v8(pp + (size_t)sl * part_slice, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) carry[i] += __ldcg(q + (size_t)i * PBM);
+        for (int i = 0; i < 8; ++i) carry[i] += v[i];
       }
+      BWD_MARK(10);
     }
   }
   tc_fence_before();
@@ -731,6 +764,7 @@ int gru_persist_bwd(const float* dout, long lddout, int dir_stride, const float*
     p.dout = dout; p.lddout = lddout; p.dir_stride = dir_stride; p.out = out; p.gates = gates;
     p.whh = whh_f; p.whh_dstride = whh_dstride; p.dgi = dgi; p.dgh = dgh; p.part = part; p.cnt = cnt;
     p.B = B; p.T = T; p.H = H; p.Kpad = kpad_of(H); p.S = S; p.nbt = nbt_all; p.bt0 = t0; p.x3 = x3;
+    p.dbg = (umma::g_dbg_flags & 8) ? 1 : 0;
     S2AG_LAUNCH(kfn, dim3(S, nbt, 2), PTHREADS, bwd_smem_bytes(H), stream, p);
   }
   return S2AG_OK;

@@ -86,7 +86,7 @@ def check_grads(named_grads, ref_grads, tol=2e-3, what=""):
     the pre-activations, so a handful of the ~1e5-1e6 ReLU/LeakyReLU inputs of a pass land on the other side of 0
     and each flip moves ONE gradient element by O(1) of its size (a conv-bias gradient channel by a few %).
     Criteria (a real kernel bug -- wrong tap, missing term, bf16-only operand -- violates all three):
-      * per tensor: at most max(2, 3%) of the elements off by more than tol * (tensor max + 1e-3 global max);
+      * per tensor: at most max(4, 3%) of the elements off by more than tol * (tensor max + 1e-3 global max);
       * per tensor: relative L2 error <= 10 * tol;
       * all tensors together: relative L2 error <= tol."""
     gmax = max([v.abs().max().item() for v in ref_grads.values()] + [1e-30])
@@ -103,7 +103,7 @@ def check_grads(named_grads, ref_grads, tol=2e-3, what=""):
         ref2 = r.pow(2).sum().item()
         num += l2
         den += ref2
-        if n_off > max(2, 0.03 * d.numel()):
+        if n_off > max(4, 0.03 * d.numel()):
             bad.append((name, "outliers", n_off, d.numel(), d.max().item(), r.abs().max().item()))
         if l2 ** 0.5 > 10 * tol * (ref2 ** 0.5 + 1e-3 * gmax * d.numel() ** 0.5):
             bad.append((name, "relL2", (l2 / max(ref2, 1e-60)) ** 0.5))
