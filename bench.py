@@ -214,7 +214,8 @@ def main():
         print(json.dumps({"roofline": roofline(args.batch_per_gpu, dev, lib)}))
         return
 
-    cfg, O = cfg_namespace()
+    from speech2affective_gestures_b200.config import namespace as config_namespace
+    cfg = config_namespace()  # (the oracle is only imported by the CPU legs below)
     B = args.batch_per_gpu
     pargs = NS(no_cuda=False, work_dir_s2ag=None, save_log=False, print_log=False, train_s2ag=True, batch_size=B,
                s2ag_num_epoch=1, val_interval=1, save_interval=10)

@@ -184,6 +184,50 @@ extern "C" int s2ag_seed_advance(uint64_t* seed_dev, uint64_t inc, void* stream)
   return S2AG_OK;
 }
 
+
+// ------------------------------------------------------------------ direct Conv1d for tiny Cin*K (WavEncoder conv1)
+// y[n, lo, co] = act(b[co] + sum_{k,c} x[n, lo*s + k - p, c] * w[co, c, k]);  one thread = one output position, all
+// Cout channels (weights in shared memory as [c*K + k][Cout]).  The implicit-GEMM engines waste their tiles on a
+// contraction of length 15: this one is bound by writing y (16 channels x 4 bytes per position).
+constexpr int DC_MAX_CK = 64, DC_MAX_CO = 32;
+__global__ void __launch_bounds__(256) conv1d_direct_kernel(const float* __restrict__ x, long ldpix_x, int L, int Cin,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ y, long ldpix_y, int Lo, int Cout, int K,
+                                                            int stride, int pad, long total, int act, float slope) {
+  __shared__ float ws[DC_MAX_CK * DC_MAX_CO];
+  __shared__ float bs[DC_MAX_CO];
+  const int CK = Cin * K;
+  for (int i = threadIdx.x; i < CK * Cout; i += blockDim.x) {
+    const int co = i % Cout, ck = i / Cout;   // ck = c*K + k ; reference weight [co][c][k]
+    ws[ck * Cout + co] = w[(long)co * CK + ck];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  for (long pos = blockIdx.x * (long)blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    const int lo = (int)(pos % Lo); const long n = pos / Lo;
+    float acc[DC_MAX_CO];
+#pragma unroll
+    for (int co = 0; co < DC_MAX_CO; ++co) acc[co] = co < Cout ? bs[co] : 0.f;
+    const int l0 = lo * stride - pad;
+    for (int k = 0; k < K; ++k) {
+      const int l = l0 + k;
+      if (l < 0 || l >= L) continue;
+      const float* xp = x + (n * L + l) * ldpix_x;
+      for (int c = 0; c < Cin; ++c) {
+        const float xv = __ldg(xp + c);
+        const float* wr = ws + (c * K + k) * Cout;
+#pragma unroll
+        for (int co = 0; co < DC_MAX_CO; ++co)
+          if (co < Cout) acc[co] = fmaf(xv, wr[co], acc[co]);
+      }
+    }
+    float* yp = y + pos * ldpix_y;
+#pragma unroll
+    for (int co = 0; co < DC_MAX_CO; ++co)
+      if (co < Cout) yp[co] = s2ag_act(acc[co], act, slope);
+  }
+}
+
 // ------------------------------------------------------------------ Conv (channels-last implicit GEMM)
 static inline int conv_out(int L, int k, int s, int p, int d) { return (L + 2 * p - d * (k - 1) - 1) / s + 1; }
 
@@ -195,6 +239,15 @@ extern "C" int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, 
   S2AG_CHECK_ARG(sh > 0 && sw > 0 && dh > 0 && dw > 0 && ldpix_x >= Cin && ldpix_y >= Cout);
   int Ho = conv_out(H, KH, sh, ph, dh), Wo = conv_out(W, KW, sw, pw, dw);
   S2AG_CHECK_ARG(Ho > 0 && Wo > 0);
+  if (W == 1 && KW == 1 && dh == 1 && Cin * KH <= DC_MAX_CK && Cout <= DC_MAX_CO && Cin * KH < 32) {
+    // contraction shorter than one tensor-core k-block: direct kernel
+    const long total = (long)N * Ho;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    auto kfn = &conv1d_direct_kernel;
+    S2AG_LAUNCH(kfn, blocks, 256, 0, stream, x, ldpix_x, H, Cin, w, bias, y, ldpix_y, Ho, Cout, KH, sh, ph, total, act, slope);
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
 #ifndef S2AG_EMU
   if (g_engine == 0 && sh == 1 && sw == 1 && dh == 1 && dw == 1 &&
       conv_shift_launch(x, ldpix_x, N, H, W, Cin, w, 0, Cin, bias, y, ldpix_y, Cout, KH, KW, ph, pw, Ho, Wo, act, slope, 0,

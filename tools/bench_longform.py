@@ -21,12 +21,12 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=64)
     a = ap.parse_args()
-    import s2ag_oracle as O
     from speech2affective_gestures_b200 import _C
     from speech2affective_gestures_b200.processor_v2 import Processor
     from speech2affective_gestures_b200.synthetic import make_data_loader
     dev = torch.device("cuda:0")
-    cfg = NS(**O.CFG)
+    from speech2affective_gestures_b200.config import namespace as config_namespace
+    cfg = config_namespace()
     pargs = NS(no_cuda=False, work_dir_s2ag=None, save_log=False, print_log=False, train_s2ag=True, batch_size=a.batch,
                s2ag_num_epoch=1, val_interval=1, save_interval=10)
     pr = Processor(ROOT, pargs, cfg, make_data_loader(8, 8, 8, n_words=20000, n_speakers=1370), 27, 3, 16000)
@@ -53,6 +53,7 @@ def main():
     # CPU arm: oracle PoseGenerator eval forward on a bounded sample, all host threads
     cpu = None
     if a.cpu_sample > 0:
+        import s2ag_oracle as O  # CPU arm only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from common import sd_cpu
         torch.set_num_threads(os.cpu_count() or 1)

@@ -8,13 +8,11 @@ from types import SimpleNamespace as NS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 
 from speech2affective_gestures_b200 import _C, ops  # noqa: E402
 from speech2affective_gestures_b200.net import multimodal_context_net_v2 as M  # noqa: E402
 from speech2affective_gestures_b200.synthetic import Vocab, synthetic_batch  # noqa: E402
-import s2ag_oracle as O  # noqa: E402
 
 
 def timeit(fn, reps=5, warm=2):
@@ -41,7 +39,8 @@ def main():
     lib.s2ag_set_precision(a.precision)
     dev = torch.device("cuda:0")
     B, T = a.batch, 34
-    cfg = NS(**O.CFG)
+    from speech2affective_gestures_b200.config import namespace as config_namespace
+    cfg = config_namespace()
     spk = Vocab("vid", 1370)
     G = M.PoseGenerator(cfg, 27, 20000, 300, None, 71, 37, 34, z_obj=spk).to(dev)
     Tn = M.PoseGeneratorTriModal(cfg, 27, 20000, 300, None, z_obj=spk).to(dev)
