@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(CTHREADS, 2) conv_shift_kernel(Params p) {
   const int n_acc = KK < NISS ? KK : NISS;
   const bool vec_src = (p.ldpix_x & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
   const int HpWp = p.Hp * p.Wp;
+  const bool vec_dst = (p.ldpix_y & 7) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
 
   uint32_t parity = 0;
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, parity ^= 1u) {
@@ -192,14 +193,32 @@ __global__ void __launch_bounds__(CTHREADS, 2) conv_shift_kernel(Params p) {
           }
         }
         if (ok) {
+          if (vec_dst && c0 + 8 <= p.Cout) {
+            // 8 consecutive channels of one pixel = one 32-byte sector
+            float val[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            if (c < p.Cout) {
-              float val = acc[i];
-              if (p.bias) val += __ldg(p.bias + c);
-              val = s2ag_act(val, p.act, p.slope);
-              if (p.accumulate) dst[c] += val; else dst[c] = val;
+            for (int i = 0; i < 8; ++i) {
+              val[i] = acc[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+              val[i] = s2ag_act(val[i], p.act, p.slope);
+            }
+            if (p.accumulate) {
+              const float4 o0 = *reinterpret_cast<const float4*>(dst + c0), o1 = *reinterpret_cast<const float4*>(dst + c0 + 4);
+              val[0] += o0.x; val[1] += o0.y; val[2] += o0.z; val[3] += o0.w;
+              val[4] += o1.x; val[5] += o1.y; val[6] += o1.z; val[7] += o1.w;
+            }
+            asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(val[0]), "f"(val[1]), "f"(val[2]),
+                         "f"(val[3]), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]), "l"(dst + c0)
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = c0 + i;
+              if (c < p.Cout) {
+                float val = acc[i];
+                if (p.bias) val += __ldg(p.bias + c);
+                val = s2ag_act(val, p.act, p.slope);
+                if (p.accumulate) dst[c] += val; else dst[c] = val;
+              }
             }
           }
         }

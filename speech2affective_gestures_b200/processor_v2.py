@@ -190,8 +190,7 @@ class Processor(object):
             with torch.no_grad():  # the reference builds and discards this graph; only .detach() is used (:809)
                 out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared_ng)
             with torch.set_grad_enabled(train):
-                dis_real = D(target_poses, in_text)
-                dis_fake = D(out_for_d, in_text)
+                dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
             if train:
                 torch.autograd.backward([dis_real, dis_fake], [g_real, g_fake])

@@ -69,3 +69,34 @@ def test_bf16x1_mode_is_bf16_close():
     out_1, _ = _run("G", 8, engine=0, precision=1)
     r = rel(out_1, out_3)
     assert 1e-6 < r < 3e-2, r  # really a different (single-pass bf16) computation, and still close
+
+
+def test_persistent_gru_batch_chunking_matches_per_step_kernels():
+    """B = 400 clips at H = 300 needs 4 batch tiles x 19 slices x 2 directions = 152 CTAs > 148: the persistent
+    recurrence / BPTT run as two launches (3 + 1 tiles).  Forward output and all gradients must match the per-step
+    SIMT kernels (s2ag_set_engine(1))."""
+    from speech2affective_gestures_b200 import ops
+    dev = torch.device("cuda:0")
+    lib = _C.lib()
+    B, T, In, H = 400, 34, 24, 300
+    g = torch.Generator().manual_seed(5)
+    base = [torch.randn(3 * H, In, generator=g) * 0.1, torch.randn(3 * H, H, generator=g) * 0.05,
+            torch.randn(3 * H, generator=g) * 0.1, torch.randn(3 * H, generator=g) * 0.1] * 2
+    x0 = torch.randn(B, T, In, generator=g)
+    gy = torch.randn(B, T, 2 * H, generator=g).to(dev)
+    res = []
+    for engine in (1, 0):
+        assert lib.s2ag_set_engine(engine) == 0
+        try:
+            ps = [t.clone().to(dev).requires_grad_(True) for t in base]
+            x = x0.clone().to(dev).requires_grad_(True)
+            y = ops.bigru(x, ps, 1, H, 0.0, False)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), x.grad.clone(), [p.grad.clone() for p in ps]))
+        finally:
+            lib.s2ag_set_engine(0)
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert rel(y0, y1) < 2e-5 and rel(dx0, dx1) < 2e-4
+    for a, b in zip(g0, g1):
+        assert rel(a, b) < 5e-4
