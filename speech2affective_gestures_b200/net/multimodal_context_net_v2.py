@@ -320,7 +320,14 @@ class PoseGeneratorTriModal(FlatParamNet, _SpeakerMixin):
         self.do_flatten_parameters = False
         self.flatten_parameters_()
 
-    def forward(self, pre_seq, in_text, in_audio, vid_indices=None):
+    def encode_inputs(self, in_text, in_audio):
+        """WavEncoder + TextEncoderTCN features (the part of forward() that depends only on the inputs); lets a
+        driver run them ahead of / beside other work and hand them to forward(..., pre=...)."""
+        a = self.audio_encoder(in_audio) if self.input_context in ('both', 'audio') else None
+        t = self.text_encoder(in_text)[0] if self.input_context in ('both', 'text') else None
+        return a, t
+
+    def forward(self, pre_seq, in_text, in_audio, vid_indices=None, pre=None):
         B, T = pre_seq.shape[0], pre_seq.shape[1]
         buf = torch.empty(B, T, self.in_size, dtype=torch.float32, device=pre_seq.device)
         pieces, slices = [], []
@@ -329,10 +336,18 @@ class PoseGeneratorTriModal(FlatParamNet, _SpeakerMixin):
         if pre_seq.requires_grad:
             raise NotImplementedError("gradient w.r.t. pre_seq is not on the reference path")
         if self.input_context in ('both', 'audio'):
-            a = self.audio_encoder(in_audio, out=ops.col_slice(buf, col, col + 32))
+            if pre is None:
+                a = self.audio_encoder(in_audio, out=ops.col_slice(buf, col, col + 32))
+            else:
+                a = pre[0]
+                buf[:, :, col:col + 32].copy_(a.detach())
             pieces.append(a); slices.append((col, col + 32)); col += 32
         if self.input_context in ('both', 'text'):
-            t, _ = self.text_encoder(in_text, out=ops.col_slice(buf, col, col + 32))
+            if pre is None:
+                t, _ = self.text_encoder(in_text, out=ops.col_slice(buf, col, col + 32))
+            else:
+                t = pre[1]
+                buf[:, :, col:col + 32].copy_(t.detach())
             if self.input_context == 'both':
                 assert a.shape[1] == t.shape[1]
             pieces.append(t); slices.append((col, col + 32)); col += 32
@@ -396,7 +411,12 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
             a = self.audio_encoder(in_mfcc) if self.input_context in ('both', 'audio') else None
         return p, a
 
-    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None, shared=None):
+    def encode_text(self, in_text):
+        """TextEncoderTCN features [B, T, 32] for forward(..., text_feat=...): depends only on the tokens and the
+        weights, so a driver may evaluate it on a side stream while the recurrent kernels of another pass run."""
+        return self.text_encoder(in_text)[0]
+
+    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None, shared=None, text_feat=None):
         B, T = pre_seq.shape[0], pre_seq.shape[1]
         buf = torch.empty(B, T, self.in_size, dtype=torch.float32, device=pre_seq.device)
         pieces, slices = [], []
@@ -415,7 +435,11 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
                 buf[:, :, col:col + 32].copy_(a.detach())
             pieces.append(a); slices.append((col, col + 32)); col += 32
         if self.input_context in ('both', 'text'):
-            t, _ = self.text_encoder(in_text, out=ops.col_slice(buf, col, col + 32))
+            if text_feat is None:
+                t, _ = self.text_encoder(in_text, out=ops.col_slice(buf, col, col + 32))
+            else:
+                t = text_feat
+                buf[:, :, col:col + 32].copy_(t.detach())
             if self.input_context == 'both':
                 assert a.shape[1] == t.shape[1], \
                     'Audio and text features must have the same number of time steps. ' \

@@ -131,6 +131,8 @@ class Processor(object):
         self._init_distributed()
         self.metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
+        self._side_stream = None
+        self.use_side_stream = True
         self.injected_rand_idx = None  # parity harness: fixed speaker permutation for processor_v2.py:903
 
     # ------------------------------------------------------------------ optimiser / distributed state
@@ -182,13 +184,46 @@ class Processor(object):
         with torch.set_grad_enabled(train):
             shared = G.encode_shared(pre_seq, in_mfcc, repeats=n_passes if G.training else 1)
         shared_ng = tuple(None if t is None else t.detach() for t in shared)
+        # Input-only encoders (the generator's TextEncoderTCN for each of its passes, the frozen baseline's WavEncoder
+        # and TextEncoderTCN) run on a side stream: they overlap the latency-bound recurrent kernels of the main
+        # stream, which occupy only about half of the SMs.  Events order each consumer after its producer; autograd
+        # runs the backward of the side-stream ops on the side stream and synchronises by itself.
+        use_side = self.device.type == "cuda" and self.use_side_stream
+        main_s = torch.cuda.current_stream() if use_side else None
+        txt1 = txt2 = txt3 = tri_pre = None
+        ev = {}
+        if use_side:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main_s)
+            with torch.cuda.stream(side):
+                if gan_on:
+                    with torch.no_grad():
+                        txt1 = G.encode_text(in_text)
+                    ev[1] = torch.cuda.Event(); ev[1].record(side)
+                with torch.no_grad():
+                    tri_pre = Tri.encode_inputs(in_text, in_audio)
+                ev['t'] = torch.cuda.Event(); ev['t'].record(side)
+                with torch.set_grad_enabled(train):
+                    txt2 = G.encode_text(in_text)
+                ev[2] = torch.cuda.Event(); ev[2].record(side)
+                if use_div:
+                    with torch.no_grad():
+                        txt3 = G.encode_text(in_text)
+                    ev[3] = torch.cuda.Event(); ev[3].record(side)
+            for t_ in (txt1, txt2, txt3) + (tuple(tri_pre) if tri_pre is not None else ()):
+                if t_ is not None:
+                    t_.record_stream(main_s)
 
         # ---- train D (processor_v2.py:791-814)
         if gan_on:
             if train:
                 D.zero_grad()
+            if use_side:
+                main_s.wait_event(ev[1])
             with torch.no_grad():  # the reference builds and discards this graph; only .detach() is used (:809)
-                out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared_ng)
+                out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared_ng, text_feat=txt1)
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
@@ -201,10 +236,14 @@ class Processor(object):
         # ---- train G (processor_v2.py:816-941)
         if train:
             G.zero_grad()
+        if use_side:
+            main_s.wait_event(ev['t'])
         with torch.no_grad():
-            out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices)
+            out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
+        if use_side:
+            main_s.wait_event(ev[2])
         with torch.set_grad_enabled(train):
-            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared)
+            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2)
             # D's own parameter gradients from this pass are discarded by the reference (zero_grad at the
             # next D step, :794), so they are not computed; gradients still flow through D into G.
             d_params = [p for p in D.parameters() if p.requires_grad]
@@ -225,8 +264,10 @@ class Processor(object):
                 rand_vids = vid_indices[rand_idx]
             else:
                 rand_vids = None
+            if use_side:
+                main_s.wait_event(ev[3])
             with torch.no_grad():  # only used detached (:913, :919)
-                out_rand, z_rand, _, _ = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng)
+                out_rand, z_rand, _, _ = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng, text_feat=txt3)
         use_kld = use_div and cfg.z_type == 'speaker'
         weights = (cfg.loss_regression_weight, cfg.loss_kld_weight if use_kld else 0.0,
                    cfg.loss_reg_weight if use_div else 0.0, cfg.loss_gan_weight if gan_on else 0.0)
@@ -241,9 +282,14 @@ class Processor(object):
             if use_kld:
                 outs += [z_mu, z_log_var]; grads += [g_mu, g_lv]
             torch.autograd.backward(outs, grads)
+            if use_side:
+                # the text-encoder backward (and its in-kernel parameter-gradient accumulation) ran on the side stream
+                main_s.wait_stream(self._side_stream)
             self._allreduce_grads(G)
             ops.adam_step(G.flat_params, G.flat_grads, self.gen_m, self.gen_v, self.lr_s2ag_gen, 0.5, 0.999, 1e-8,
                           self.gen_step, 1.0 / self.world)
+        if use_side:
+            main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
         ops.l1_mean(out.detach(), target_poses, m[M_L1:M_L1 + 1])
         ops.l1_mean(out_tri, target_poses, m[M_L1_TRI:M_L1_TRI + 1])
         self.last_out, self.last_out_trimodal = out.detach(), out_tri
