@@ -171,6 +171,9 @@ int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const floa
  * row of stride lddout (dir_stride = H normally; 0 when both halves share the gradient of their
  * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += ; pass all eight as NULL to
  * skip the parameter gradients (discriminator inside the generator step).
+ * phases (bit mask): 1 = the recurrence (BPTT; fills the dgi/dgh rows in ws), 2 = dx from dgi, 4 = the time-batched weight / bias
+ * gradients from dgi/dgh.  7 = everything; a caller may issue 3 on its main stream and 4 on a second stream (ordered after
+ * the first call) so that the weight-gradient GEMMs overlap the next layer's latency-bound recurrence.
  * ws: float[s2ag_gru_bwd_ws_floats(B,T,H)] = B*T*6H (dgi) + B*T*6H (dgh) + 4*B*H (dh ping-pong) + the partial-product
  * exchange buffers of the persistent tcgen05 BPTT kernel */
 long s2ag_gru_bwd_ws_floats(int B, int T, int H);
@@ -179,7 +182,7 @@ int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride, const flo
                        const float* w_ih_f, const float* w_ih_r, const float* w_hh_f, const float* w_hh_r,
                        float* dx, long lddx, float* dw_ih_f, float* dw_ih_r, float* db_ih_f, float* db_ih_r,
                        float* dw_hh_f, float* dw_hh_r, float* db_hh_f, float* db_hh_r, float* ws,
-                       int B, int T, int In, int H, void* stream);
+                       int B, int T, int In, int H, int phases, void* stream);
 
 /* ---- speaker style vector (:513-516, :536-539; net/embedding_net.py:10-13) -------------------
  * z = mu + eps * exp(0.5*logvar); z[B,Z] is also tiled over T into dst[B,T,ld] columns [off, off+Z) */

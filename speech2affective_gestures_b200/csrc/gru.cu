@@ -187,8 +187,10 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
                                   const float* w_ih_f, const float* w_ih_r, const float* w_hh_f, const float* w_hh_r,
                                   float* dx, long lddx, float* dw_ih_f, float* dw_ih_r, float* db_ih_f, float* db_ih_r,
                                   float* dw_hh_f, float* dw_hh_r, float* db_hh_f, float* db_hh_r, float* ws,
-                                  int B, int T, int In, int H, void* stream) {
+                                  int B, int T, int In, int H, int phases, void* stream) {
   S2AG_CHECK_ARG(dout && x && out && gates && w_ih_f && w_ih_r && w_hh_f && w_hh_r && ws);
+  S2AG_CHECK_ARG(phases > 0 && phases < 8);
+  const bool do_rec = phases & 1, do_dx = phases & 2, do_w = phases & 4;
   const bool want_w = dw_ih_f != nullptr;  // all eight weight-gradient pointers or none
   S2AG_CHECK_ARG(!want_w || (dw_ih_r && db_ih_f && db_ih_r && dw_hh_f && dw_hh_r && db_hh_f && db_hh_r));
   S2AG_CHECK_ARG(B >= 0 && T > 0 && In > 0 && H > 0 && ldx >= In);
@@ -202,14 +204,14 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
   auto kg = &gru_bwd_gate_kernel;
   bool persistent = false;
 #ifndef S2AG_EMU
-  if (g_engine == 0 && gru_persist_bwd_ws_bytes(B, H) > 0) {
+  if (do_rec && g_engine == 0 && gru_persist_bwd_ws_bytes(B, H) > 0) {
     int rc = gru_persist_bwd(dout, lddout, dir_stride, out, gates, w_hh_f, (long)(w_hh_r - w_hh_f), dgi, dgh,
                              carry[0] + 4L * B * H, B, T, H, umma::g_precision == 0 ? 1 : 0, stream);
     if (rc != S2AG_OK) { s2ag_set_error("gru_persist_bwd failed (%d)", rc); return rc; }
     persistent = true;
   }
 #endif
-  for (int s = 0; s < T && !persistent; ++s) {
+  for (int s = 0; s < T && !persistent && do_rec; ++s) {
     float* cin = carry[s & 1];
     float* cout = carry[(s + 1) & 1];
     S2AG_LAUNCH(kg, eblocks, 256, 0, stream, dout, lddout, dir_stride, out, gates, (const float*)cin, cout, dgi, dgh,
@@ -231,7 +233,7 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
   float* db_ih[2] = {db_ih_f, db_ih_r};
   float* dw_hh[2] = {dw_hh_f, dw_hh_r};
   float* db_hh[2] = {db_hh_f, db_hh_r};
-  for (int d = 0; d < 2 && want_w; ++d) {
+  for (int d = 0; d < 2 && want_w && do_w; ++d) {
     {  // dW_ih[d][3H, In] += dgi_d^T @ x
       LdPlain<false> a{dgi + (long)d * 3 * H, 1, 6L * H, 0};
       LdPlain<false> b{x, 1, ldx, 0};
@@ -248,7 +250,7 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
       launch_colsum(dgh + (long)d * 3 * H, 6L * H, db_hh[d], M, 3 * H, stream);
     }
   }
-  if (dx) {
+  if (dx && do_dx) {
     for (int d = 0; d < 2; ++d) {
       LdPlain<true> a{dgi + (long)d * 3 * H, 6L * H, 1, 0};
       LdPlain<false> b{w_ih[d], 1, (long)In, 0};

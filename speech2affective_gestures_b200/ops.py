@@ -212,6 +212,14 @@ class _BnState:
 
 
 _bn_repeat = [1]
+_side_stream = [None]
+
+
+def set_side_stream(stream):
+    """Second CUDA stream for work that is off the critical path of the recurrent kernels (weight-gradient GEMMs of a
+    GRU layer).  The caller must make its main stream wait for it before consuming parameter gradients."""
+    _side_stream[0] = stream
+
 
 
 class bn_repeat:
@@ -572,7 +580,10 @@ class BiGruFn(torch.autograd.Function):
         B, T, In0, H, nlayers, sum_halves, slices, npieces = ctx.cfg
         st = _stream(dy)
         M = B * T
-        ws = _empty((_C.lib().s2ag_gru_bwd_ws_floats(B, T, H),), dy)
+        side = _side_stream[0] if dy.is_cuda else None
+        main = torch.cuda.current_stream(dy.device) if side is not None else None
+        ws_floats = _C.lib().s2ag_gru_bwd_ws_floats(B, T, H)
+        ws = None if side is not None else _empty((ws_floats,), dy)
         if sum_halves:
             d, ldd = _rows(dy, H)
             dstride = 0
@@ -585,10 +596,27 @@ class BiGruFn(torch.autograd.Function):
             wif, whf, bif, bhf, wir, whr, bir, bhr = ctx.params[8 * l:8 * l + 8]
             need_dx = l > 0 or npieces > 0 or ctx.needs_input_grad[0]
             dxl = _empty((B, T, rec["In"]), dy) if need_dx else None
-            gw = [_p(_grad_of(q)) for q in (wif, wir, bif, bir, whf, whr, bhf, bhr)] if wif.requires_grad \
-                else [None] * 8
-            _C.call("s2ag_gru_layer_bwd", _p(d), ldd, dstride, _p(rec["x"]), rec["ldx"], _p(rec["out"]), _p(rec["gates"]),
-                    _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"], *gw, _p(ws), B, T, rec["In"], H, st)
+            want_w = wif.requires_grad
+            gw = [_p(_grad_of(q)) for q in (wif, wir, bif, bir, whf, whr, bhf, bhr)] if want_w else [None] * 8
+            args = [_p(d), ldd, dstride, _p(rec["x"]), rec["ldx"], _p(rec["out"]), _p(rec["gates"]),
+                    _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"], *gw]
+            if side is not None and want_w:
+                # recurrence + dx on the main stream; the time-batched weight-gradient GEMMs of this layer on the
+                # side stream, overlapping the next (lower) layer's latency-bound BPTT kernel.  Per-layer workspace.
+                wsl = _empty((ws_floats,), dy)
+                _C.call("s2ag_gru_layer_bwd", *args, _p(wsl), B, T, rec["In"], H, 3, st)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                _C.call("s2ag_gru_layer_bwd", *args, _p(wsl), B, T, rec["In"], H, 4,
+                        ctypes.c_void_p(side.cuda_stream))
+                for t_ in (wsl, rec["x"], rec["out"], rec["gates"], d):
+                    if t_ is not None:
+                        t_.record_stream(side)
+            else:
+                if ws is None:
+                    ws = _empty((ws_floats,), dy)
+                _C.call("s2ag_gru_layer_bwd", *args, _p(ws), B, T, rec["In"], H, 7, st)
             if l > 0:
                 drop = ctx.layers[l - 1]["drop"]
                 if drop is not None:

@@ -196,6 +196,7 @@ class Processor(object):
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
             side = self._side_stream
+            ops.set_side_stream(side)  # GRU weight-gradient GEMMs run there, beside the next layer's BPTT kernel
             side.wait_stream(main_s)
             with torch.cuda.stream(side):
                 if gan_on:
@@ -229,6 +230,8 @@ class Processor(object):
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
             if train:
                 torch.autograd.backward([dis_real, dis_fake], [g_real, g_fake])
+                if use_side:
+                    main_s.wait_stream(self._side_stream)  # weight-gradient GEMMs issued on the side stream
                 self._allreduce_grads(D)
                 ops.adam_step(D.flat_params, D.flat_grads, self.dis_m, self.dis_v, self.lr_s2ag_dis, 0.5, 0.999,
                               1e-8, self.dis_step, 1.0 / self.world)
@@ -290,6 +293,7 @@ class Processor(object):
                           self.gen_step, 1.0 / self.world)
         if use_side:
             main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
+            ops.set_side_stream(None)
         ops.l1_mean(out.detach(), target_poses, m[M_L1:M_L1 + 1])
         ops.l1_mean(out_tri, target_poses, m[M_L1_TRI:M_L1_TRI + 1])
         self.last_out, self.last_out_trimodal = out.detach(), out_tri
