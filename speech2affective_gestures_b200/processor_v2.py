@@ -132,6 +132,7 @@ class Processor(object):
         self.metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
         self._side_stream = None
+        self._side_stream_b = None
         self.use_side_stream = True
         self.injected_rand_idx = None  # parity harness: fixed speaker permutation for processor_v2.py:903
 
@@ -225,6 +226,27 @@ class Processor(object):
                 main_s.wait_event(ev[1])
             with torch.no_grad():  # the reference builds and discards this graph; only .detach() is used (:809)
                 out_for_d, *_ = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared_ng, text_feat=txt1)
+            if use_side:
+                # The frozen baseline's recurrent body runs on a second side stream beside the D step.  Its persistent GRU
+                # kernels (76 resident CTAs, one SM each) may only overlap the discriminator-sized persistent kernels of
+                # the D step (<= 32 small CTAs): it starts after generator pass #1 (event below) and the main stream waits
+                # for it before generator pass #2, so two generator-sized persistent kernels (76 + 76 > 148 SMs) can
+                # never be in flight together.
+                if self._side_stream_b is None:
+                    self._side_stream_b = torch.cuda.Stream()
+                sb = self._side_stream_b
+                ev_p1 = torch.cuda.Event(); ev_p1.record(main_s)
+                sb.wait_event(ev_p1)
+                sb.wait_event(ev['t'])
+                with torch.cuda.stream(sb):
+                    with torch.no_grad():
+                        out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
+                ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
+                out_tri.record_stream(main_s)
+                for t_ in tri_pre:
+                    if t_ is not None:
+                        t_.record_stream(sb)
+                pre_seq.record_stream(sb)
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
@@ -239,10 +261,13 @@ class Processor(object):
         # ---- train G (processor_v2.py:816-941)
         if train:
             G.zero_grad()
-        if use_side:
-            main_s.wait_event(ev['t'])
-        with torch.no_grad():
-            out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
+        if use_side and 'tdone' in ev:
+            main_s.wait_event(ev['tdone'])
+        else:
+            if use_side:
+                main_s.wait_event(ev['t'])
+            with torch.no_grad():
+                out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
         if use_side:
             main_s.wait_event(ev[2])
         with torch.set_grad_enabled(train):
@@ -293,6 +318,8 @@ class Processor(object):
                           self.gen_step, 1.0 / self.world)
         if use_side:
             main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
+            if self._side_stream_b is not None:
+                main_s.wait_stream(self._side_stream_b)
             ops.set_side_stream(None)
         ops.l1_mean(out.detach(), target_poses, m[M_L1:M_L1 + 1])
         ops.l1_mean(out_tri, target_poses, m[M_L1_TRI:M_L1_TRI + 1])
