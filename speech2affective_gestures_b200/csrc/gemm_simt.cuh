@@ -60,6 +60,22 @@ struct LdPlain {
       for (int i = 0; i < 8; ++i) v[i] = __ldg(c.q + i * ld_k);
     }
   }
+  // FAST path of the tcgen05 engine: the host verified that EVERY row segment is 32-byte aligned (fast_ok), so an item
+  // is exactly one LDG.E.256 with no per-thread alignment state
+  static constexpr bool kHasFast = KCONTIG;
+  bool fast_ok() const {
+    return KCONTIG && ld_k == 1 && (reinterpret_cast<unsigned long long>(p) & 31ull) == 0 && (ld_row & 7) == 0 &&
+           (bstride & 7) == 0;
+  }
+  __device__ __forceinline__ void load8_fast(const Cur& c, float (&v)[8]) const {
+#ifndef S2AG_EMU
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(c.q));
+#else
+    load8_full(c, v);
+#endif
+  }
   __device__ __forceinline__ void load8(const Cur& c, int kend, float (&v)[8]) const {
     if (c.k + 8 <= kend) {
       load8_full(c, v);
@@ -80,6 +96,9 @@ template <int ORDER>
 struct LdConv {
   static constexpr bool kContig = true;
   static constexpr int kOrder = ORDER;
+  static constexpr bool kHasFast = false;
+  bool fast_ok() const { return true; }
+  template <class C> __device__ __forceinline__ void load8_fast(const C& c, float (&v)[8]) const { load8_full(c, v); }
   const float* x; int H, W, C;       // source geometry
   int Ho, Wo;                        // row space geometry
   int KH, KW, sh, sw, dh, dw, sgn, off_h, off_w;
@@ -169,6 +188,9 @@ struct LdConv {
 template <class L>
 struct LdT {
   static constexpr bool kContig = !L::kContig;
+  static constexpr bool kHasFast = false;
+  bool fast_ok() const { return true; }
+  template <class C> __device__ __forceinline__ void load8_fast(const C& c, float (&v)[8]) const { load8_full(c, v); }
   L l;
   __device__ __forceinline__ float operator()(int b, int row, int k) const { return l(b, k, row); }
   struct Cur { int c, kh, kw, p, n, ho, wo; };
@@ -207,6 +229,9 @@ struct LdT {
 template <int ORDER>
 struct LdWdgrad {
   static constexpr bool kContig = false;  // consecutive k are strided in memory; consecutive rows (c_in) are the near axis
+  static constexpr bool kHasFast = false;
+  bool fast_ok() const { return true; }
+  template <class C> __device__ __forceinline__ void load8_fast(const C& c, float (&v)[8]) const { load8_full(c, v); }
   const float* w; int Cout, KK; long s_co, s_c, s_kk;
   __device__ __forceinline__ void split_k(int k, int& co, int& kk) const {
     if (ORDER == ORDER_CKK) { kk = k % KK; co = k / KK; } else { co = k % Cout; kk = k / Cout; }
@@ -245,6 +270,9 @@ struct LdWdgrad {
 // channels; the weight tensor is small and cache-resident, its strided reads are cheap.)
 struct LdWkkc {
   static constexpr bool kContig = true;
+  static constexpr bool kHasFast = false;
+  bool fast_ok() const { return true; }
+  template <class C> __device__ __forceinline__ void load8_fast(const C& c, float (&v)[8]) const { load8_full(c, v); }
   const float* w; int Cin, KK;
   __device__ __forceinline__ float operator()(int, int row, int k) const {
     const int c = k % Cin, tap = k / Cin;

@@ -10,13 +10,15 @@
 // tensor core accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  in fp32 in TMEM ("bf16x3", ~2^-17
 // relative operand error).  precision mode 1 ("bf16x1") drops the two correction terms.
 //
-// Structure of one CTA (512 threads, one 128 x BN output tile, BN <= 256 a multiple of 16):
-//   - all 16 warps stage: global -> registers (three rotating register sets: the loads of the next TWO
-//     k-blocks are in flight while the current one is converted) -> bf16 hi/lo -> shared memory in the
-//     canonical no-swizzle K-major UMMA layout [k-chunk of 8][row][16 B], two stages;
-//   - fence.proxy.async + __syncthreads, then ONE thread issues the tcgen05.mma instructions of the
-//     stage (M=128, N=BN, K=16 each) and tcgen05.commit's the stage's "empty" mbarrier, so the
-//     tensor core works on stage s while the warps stage s^1;
+// Structure of one CTA (544 threads, one 128 x BN output tile, BN <= 256 a multiple of 16):
+//   - 16 staging warps: global -> registers (two ping-pong register sets: the loads of the next k-block
+//     are in flight while the current one is converted) -> bf16 hi/lo -> shared memory in the canonical
+//     no-swizzle K-major UMMA layout [k-chunk of 8][row][16 B], two stages; each warp fences
+//     (fence.proxy.async) and arrives on the stage's "full" mbarrier;
+//   - a 17th warp's elected thread waits for "full", issues the tcgen05.mma instructions of the stage
+//     (M=128, N=BN, K=16 each; a thread issues only about one tcgen05.mma per 160 cycles, so the issue
+//     must not sit on the staging warps' path) and tcgen05.commit's the stage's "empty" mbarrier: the
+//     tensor core works on stage s while the warps stage s^1, with no block-wide barrier in the loop;
 //   - accumulator: BN fp32 columns x 128 lanes of TMEM; epilogue: tcgen05.ld (32 lanes x 32
 //     columns per warp), transposed through shared memory so that global stores (and the
 //     epilogue's bias / residual loads) are coalesced along n.
@@ -29,7 +31,7 @@
 namespace s2ag {
 namespace umma {
 
-constexpr int BM = 128, BK = 32, THREADS = 512, BN_MAX = 256, EPI_WARPS = 16;
+constexpr int BM = 128, BK = 32, STAGE_THREADS = 512, THREADS = 544, BN_MAX = 256, EPI_WARPS = 16;  // 16 staging warps + 1 MMA-issuer warp
 constexpr int A_STAGE_BYTES = BM * BK * 2 * 2;  // hi + lo, bf16
 constexpr int HEADER_BYTES = 128;               // mbarriers + TMEM base slot
 
@@ -60,6 +62,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
@@ -161,14 +166,19 @@ __device__ __forceinline__ void fetch_item(const Ld& ld, const typename Ld::Cur&
 
 struct RegSet { float a[8]; float b0[8]; float b1[8]; };
 
-template <class LdA, class LdB, class Epi>
+// FAST = compile-time bf16x3 and operands whose fast_ok() holds (plain rows, every row segment 32-byte aligned: one
+// LDG.E.256 per item): the staging code of all full k-blocks carries no alignment state, no tail guards and no precision
+// branches; only a final partial k-block runs the guarded path.
+template <class LdA, class LdB, class Epi, bool FAST>
 __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi epi, int M, int N, int K, int splitk,
-                                                               int BN, int x3) {
+                                                               int BN, int x3_rt) {
+  const int x3 = FAST ? 1 : x3_rt;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_empty[2] = {sbase, sbase + 8};
-  const uint32_t bar_done = sbase + 16;
+  const uint32_t bar_empty[2] = {sbase, sbase + 8};        // stage s may be overwritten (tcgen05.commit of its MMAs)
+  const uint32_t bar_done = sbase + 16;                     // all MMAs of the tile completed
+  const uint32_t bar_full[2] = {sbase + 32, sbase + 40};    // stage s staged by all 16 staging warps
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 24);
   const int b_half_bytes = BN * BK * 2;  // one of hi / lo
   const int stage_bytes = A_STAGE_BYTES + 2 * b_half_bytes;
@@ -188,6 +198,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
     mbar_init(bar_empty[0], 1);
     mbar_init(bar_empty[1], 1);
     mbar_init(bar_done, 1);
+    mbar_init(bar_full[0], STAGE_THREADS / 32);
+    mbar_init(bar_full[1], STAGE_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(sbase + 24, ncols);
@@ -195,7 +207,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc(BN);
+  const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
 
+  if (warp == STAGE_THREADS / 32) {
+    // ================= MMA issuer warp: one thread, decoupled from the staging warps by the full / empty mbarriers
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st_i = kb & 1;
+        mbar_wait(bar_full[st_i], (uint32_t)((kb >> 1) & 1));
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stage0 + st_i * stage_bytes), sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          const uint32_t a_hi = sa + j * 2 * a_lbo, a_lo = a_hi + BM * BK * 2;
+          const uint32_t b_hi = sb + j * 2 * b_lbo, b_lo = b_hi + b_half_bytes;
+          const uint64_t dah = make_desc(a_hi, a_lbo, sbo), dbh = make_desc(b_hi, b_lbo, sbo);
+          uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+          if (x3) {
+            const uint64_t dal = make_desc(a_lo, a_lbo, sbo), dbl = make_desc(b_lo, b_lbo, sbo);
+            mma_bf16(tmem_base, dal, dbh, idesc, acc);
+            mma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            acc = 1u;
+          }
+          mma_bf16(tmem_base, dah, dbh, idesc, acc);
+        }
+        mma_commit(bar_empty[st_i]);
+        if (kb + 1 == nkb) mma_commit(bar_done);
+      }
+    }
+  } else {
+  // ================= staging warps (and, afterwards, the epilogue)
   // staging assignment: one A item and up to two B items per thread (see item_coords); one cursor per item
   static_assert(BK == LD_STEP, "loader cursors advance by one k-block");
   int r, k8;
@@ -209,19 +251,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
   typename LdB::Cur cb[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const bool has = tid + i * THREADS < 4 * BN;
-    item_coords<LdB>(has ? tid + i * THREADS : 0, BN, r, k8);
+    const bool has = tid + i * STAGE_THREADS < 4 * BN;
+    item_coords<LdB>(has ? tid + i * STAGE_THREADS : 0, BN, r, k8);
     okB[i] = has && n0 + r < N;
     offB[i] = has ? (k8 * BN + r) * 16 : -1;
     kB[i] = kbeg + k8 * 8;
     cb[i] = b.cursor(batch, okB[i] ? n0 + r : 0, kB[i]);
   }
-  const uint32_t idesc = make_idesc(BN);
-  const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
-
   auto fetch = [&](int kb, RegSet& s) {
     if (kb >= nkb) return;
-    if (kb + 1 < nkb || tail_full) {
+    if (FAST && (kb + 1 < nkb || tail_full)) {
+      if (okA) a.load8_fast(ca, s.a); else { _Pragma("unroll") for (int i = 0; i < 8; ++i) s.a[i] = 0.f; }
+      if (offB[0] >= 0) { if (okB[0]) b.load8_fast(cb[0], s.b0); else { _Pragma("unroll") for (int i = 0; i < 8; ++i) s.b0[i] = 0.f; } }
+      if (offB[1] >= 0) { if (okB[1]) b.load8_fast(cb[1], s.b1); else { _Pragma("unroll") for (int i = 0; i < 8; ++i) s.b1[i] = 0.f; } }
+    } else if (kb + 1 < nkb || tail_full) {
       fetch_item<true>(a, ca, okA, kA, kend, s.a);
       if (offB[0] >= 0) fetch_item<true>(b, cb[0], okB[0], kB[0], kend, s.b0);
       if (offB[1] >= 0) fetch_item<true>(b, cb[1], okB[1], kB[1], kend, s.b1);
@@ -242,47 +285,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
     if (offB[0] >= 0) split_store(s.b0, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[0], x3 != 0);
     if (offB[1] >= 0) split_store(s.b1, st + A_STAGE_BYTES, st + A_STAGE_BYTES + b_half_bytes, offB[1], x3 != 0);
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sa = smem_u32(st), sb = sa + A_STAGE_BYTES;
-#pragma unroll
-      for (int j = 0; j < BK / 16; ++j) {
-        const uint32_t a_hi = sa + j * 2 * a_lbo, a_lo = a_hi + BM * BK * 2;
-        const uint32_t b_hi = sb + j * 2 * b_lbo, b_lo = b_hi + b_half_bytes;
-        const uint64_t dah = make_desc(a_hi, a_lbo, sbo), dbh = make_desc(b_hi, b_lbo, sbo);
-        uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-        if (x3) {
-          const uint64_t dal = make_desc(a_lo, a_lbo, sbo), dbl = make_desc(b_lo, b_lbo, sbo);
-          mma_bf16(tmem_base, dal, dbh, idesc, acc);
-          mma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          acc = 1u;
-        }
-        mma_bf16(tmem_base, dah, dbh, idesc, acc);
-      }
-      mma_commit(bar_empty[st_i]);
-      if (kb + 1 == nkb) mma_commit(bar_done);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cta(bar_full[st_i]);  // 16 arrivals (one per staging warp) complete the stage
   };
 
-  // three register sets rotate: the loads of k-blocks kb+1 and kb+2 are in flight while k-block kb is converted
-  RegSet s0, s1, s2;
+  // two register sets ping-pong: the loads of k-block kb+1 are in flight while k-block kb is converted and stored
+  // (the MMA issue is off this path, so converting one k-block already outlasts the L2 latency of the next)
+  RegSet s0, s1;
   fetch(0, s0);
-  fetch(1, s1);
-  for (int kb = 0; kb < nkb; kb += 3) {
-    fetch(kb + 2, s2);
+  for (int kb = 0; kb < nkb; kb += 2) {
+    fetch(kb + 1, s1);
     stage_and_issue(kb, s0);
     if (kb + 1 < nkb) {
-      fetch(kb + 3, s0);
+      fetch(kb + 2, s0);
       stage_and_issue(kb + 1, s1);
-    }
-    if (kb + 2 < nkb) {
-      fetch(kb + 4, s1);
-      stage_and_issue(kb + 2, s2);
     }
   }
 
-  if (nkb > 0) {
+  }  // staging warps
+  if (nkb > 0 && warp < EPI_WARPS) {
     mbar_wait(bar_done, 0);
     tc_fence_after();
     // epilogue: the stage buffers are free now (every MMA has completed); reuse them for the transposition
@@ -326,15 +347,21 @@ static inline size_t smem_bytes(int BN) {
 
 // splitk > 1 on entry means "the epilogue is linear, partial sums may be combined by atomicAdd": the engine then
 // picks its own split so that one wave of CTAs (one per SM) covers the problem.
-template <class LdA, class LdB, class Epi>
-static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
-                          void* stream) {
-  auto kfn = &gemm_umma_kernel<LdA, LdB, Epi>;
+template <class LdA, class LdB, class Epi, bool FAST>
+static inline void launch_variant(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int splitk, int BN,
+                                  dim3 grid, void* stream) {
+  auto kfn = &gemm_umma_kernel<LdA, LdB, Epi, FAST>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(BN_MAX));
     attr_set = true;
   }
+  S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0);
+}
+
+template <class LdA, class LdB, class Epi>
+static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
+                          void* stream) {
   const int BN = pick_bn(N);
   const int tiles = s2ag_cdiv(N, BN) * s2ag_cdiv(M, BM) * nbatch;
   if (splitk > 1) {
@@ -345,7 +372,19 @@ static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int
     splitk = sk;
   }
   dim3 grid(s2ag_cdiv(N, BN), s2ag_cdiv(M, BM), nbatch * splitk);
-  S2AG_LAUNCH(kfn, grid, THREADS, smem_bytes(BN), stream, a, b, epi, M, N, K, splitk, BN, g_precision == 0 ? 1 : 0);
+  // FAST variant: both operands offer a fast item load, every k-slice is a whole number of k-blocks, fp32-grade mode
+  bool fast = false;
+  if constexpr (LdA::kHasFast && LdB::kHasFast) {
+    int kper = (K + splitk - 1) / splitk;
+    kper = ((kper + BK - 1) / BK) * BK;
+    (void)kper;
+    fast = g_precision == 0 && a.fast_ok() && b.fast_ok() && !(g_dbg_flags & 16);  // (a k tail runs the guarded path)
+  }
+  if (fast) {
+    if constexpr (LdA::kHasFast && LdB::kHasFast) launch_variant<LdA, LdB, Epi, true>(a, b, epi, M, N, K, splitk, BN, grid, stream);
+  } else {
+    launch_variant<LdA, LdB, Epi, false>(a, b, epi, M, N, K, splitk, BN, grid, stream);
+  }
 }
 
 // shapes worth a tensor-core tile: anything else stays on the exact-fp32 SIMT kernel
