@@ -320,6 +320,26 @@ struct EpiGeneric {
     else if (mode == 1) *dst += v;
     else *dst = v;
   }
+  // Column-major walk used by the tcgen05 epilogue (a lane owns one output column n and visits 32 rows): everything
+  // that depends only on (batch, n) -- bias value, permuted column, base pointers -- is computed once in col().
+  struct Col { float* dst; const float* mul; float bias; };
+  __device__ __forceinline__ Col col(int b, int n) const {
+    Col c;
+    const int ncol = perm_C > 0 ? (n % perm_C) * perm_KK + n / perm_C : n;
+    c.dst = C + b * bstride + ncol;
+    c.mul = mul_src ? mul_src + n : nullptr;
+    c.bias = bias ? __ldg(bias + b * bias_bstride + n) : 0.f;
+    return c;
+  }
+  __device__ __forceinline__ void apply(const Col& c, int m, float acc, bool partial) const {
+    float v = fmaf(alpha, acc, c.bias);
+    v = s2ag_act(v, act, slope);
+    if (c.mul) v *= s2ag_act_grad_from_out(__ldg(c.mul + (long)m * ld_mul), mul_act, mul_slope);
+    float* dst = c.dst + (long)m * ldc;
+    if (partial || mode == 2) atomicAdd(dst, v);
+    else if (mode == 1) *dst += v;
+    else *dst = v;
+  }
 };
 static inline EpiGeneric make_epi(float* C, long ldc, const float* bias = nullptr, int act = 0, float slope = 0.f,
                                   int mode = 0) {

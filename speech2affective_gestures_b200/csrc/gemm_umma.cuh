@@ -319,9 +319,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
       const bool n_ok = (c0 + lane < BN) && n < N;
       const int mlim = M - (m0 + lane_base);
       if (n_ok) {
+        const typename Epi::Col cc = epi.col(batch, n);  // (batch, n)-dependent state once per column
+        const int rmax = mlim < 32 ? mlim : 32;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr)
-          if (rr < mlim) epi(batch, m0 + lane_base + rr, n, tbuf[rr * 33 + lane], splitk > 1);
+        for (int rr = 0; rr < rmax; ++rr) epi.apply(cc, m0 + lane_base + rr, tbuf[rr * 33 + lane], splitk > 1);
       }
       __syncwarp();
     }

@@ -71,6 +71,18 @@ struct EpiTcn {
     y[i] = v;
     if (out) { float o = v + __ldg(res + i); out[i] = o > 0.f ? o : 0.f; }
   }
+  struct Col { int n; float bias; unsigned long long seed; };
+  __device__ __forceinline__ Col col(int, int n) const {
+    return Col{n, __ldg(bias + n), seed + ((p > 0.f && seed_dev) ? seed_dev[0] : 0ull)};
+  }
+  __device__ __forceinline__ void apply(const Col& c, int m, float acc, bool) const {
+    const long i = (long)m * ld + c.n;
+    float v = acc + c.bias;
+    v = v > 0.f ? v : 0.f;
+    if (p > 0.f) v *= s2ag_dropout_scale(c.seed, (unsigned long long)i, p);
+    y[i] = v;
+    if (out) { float o = v + __ldg(res + i); out[i] = o > 0.f ? o : 0.f; }
+  }
 };
 
 // g_out = dout * (out>0); dx = g_out; g2 = g_out * (y2>0) * scale
