@@ -95,7 +95,7 @@ def run_reference_arm(args):
 
 
 # ncu --set full capture of the roofline launch (profiles/r01_ncu_umma_gemm.txt): dram__bytes_read.sum + dram__bytes_write.sum
-ROOFLINE_TRAFFIC_BYTES = 38267136  # 25.29 MB read + 12.98 MB written
+ROOFLINE_TRAFFIC_BYTES = 37511680  # 25.29 MB read + 12.22 MB written (final r01 capture)
 
 
 def roofline(B, dev, lib, clips_per_s_per_gpu=None):

@@ -58,7 +58,7 @@ class FlatParamNet(nn.Module):
         if not params:
             return self
         dev = params[0].device
-        n = sum((p.numel() + 3) // 4 * 4 for p in params)  # keep every tensor 16-byte aligned
+        n = sum((p.numel() + 7) // 8 * 8 for p in params)  # every tensor 32-byte aligned (one LDG.E.256 per operand item)
         flat = torch.zeros(n, dtype=torch.float32, device=dev)
         grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
@@ -69,7 +69,7 @@ class FlatParamNet(nn.Module):
                 grad[off:off + k].copy_(p.grad.reshape(-1))
             p.data = flat[off:off + k].view(p.shape)
             p.grad = grad[off:off + k].view(p.shape)
-            off += (k + 3) // 4 * 4
+            off += (k + 7) // 8 * 8
         self._flat, self._flat_grad = flat, grad
         return self
 
