@@ -95,7 +95,8 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
 // slice by slice as the producing CTAs publish it (per-slice release/acquire flags, cp.async.cg + mbarrier
 // arrive-on-completion) and run the gate-math epilogue; warp 8 issues the tcgen05.mma k-step of a slice as soon as
 // that slice has landed, so only the LAST slice to arrive is on the critical path of a time step.
-constexpr int FWD_THREADS = 384, FWD_HDR = 512, MAX_SLICES = 24, NISSUE = 4;  // 8 worker warps + 4 MMA-issuer warps
+// 8 worker warps + 4 MMA-issuer warps
+constexpr int FWD_THREADS = 384, FWD_HDR = 512, MAX_SLICES = 24, NISSUE = 4;
 // Back-to-back tcgen05.mma into ONE accumulator serialise on the MMA latency (~160 cycles each for these tiny N=48
 // tiles, measured): the k-steps of a time step are spread round-robin over NACC independent TMEM accumulators that
 // the epilogue sums.
@@ -103,7 +104,9 @@ constexpr int NACC = 8;  // = 2 per MMA-issuer thread
 
 // bring-up aid (s2ag_debug_flags bit 1): clock64 timeline of CTA (slice 0, tile 0, direction 0), 16 marks per step
 __device__ long long g_gru_timeline[64 * 16];
-__device__ long long g_gru_slices[64 * 3 * MAX_SLICES];  // per step: [flag seen | copy issued | landed][slice]
+__device__ long long g_gru_slices[64 * 3 * MAX_SLICES];
+__device__ long long g_gru_ctas[MAX_SLICES * 8];  // globaltimer marks of every slice CTA of group 0 at step 10
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }  // per step: [flag seen | copy issued | landed][slice]
 #define GRU_MARK(slot) do { if (dbg) g_gru_timeline[(s & 63) * 16 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -209,8 +212,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
     const int jb = j0 + u0;                  // first hidden unit of this thread
     const bool b_ok = b < B;
     // 16-byte accesses to gi / out rows: all 8 units valid and every row segment 16-byte aligned
-    const bool vec_ok = (H & 3) == 0 && jb + 8 <= H &&
+    const bool vec_ok = (H & 3) == 0 &&
                         ((reinterpret_cast<uintptr_t>(p.gi) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    // the last slice may own a partial group of units: validity per 4 units (H % 4 == 0 on this path)
+    const bool q0_ok = jb + 4 <= H, q1_ok = jb + 8 <= H;
     const float* bhh = p.bhh + dir * p.bhh_dstride;
     float br[8], bz[8], bn[8], h_own[8];
 #pragma unroll
@@ -238,8 +243,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
       if (pt < 0 || !b_ok) { pt = -1; return; }
       float* orow = p.out + ((long)b * T + pt) * 2 * H + (long)dir * H + jb;
       if (vec_ok) {
-        reinterpret_cast<float4*>(orow)[0] = make_float4(ph[0], ph[1], ph[2], ph[3]);
-        reinterpret_cast<float4*>(orow)[1] = make_float4(ph[4], ph[5], ph[6], ph[7]);
+        if (q0_ok) reinterpret_cast<float4*>(orow)[0] = make_float4(ph[0], ph[1], ph[2], ph[3]);
+        if (q1_ok) reinterpret_cast<float4*>(orow)[1] = make_float4(ph[4], ph[5], ph[6], ph[7]);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -268,9 +273,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
         const float* g = p.gi + ((long)(b_ok ? b : 0) * T + t) * 6 * H + (long)dir * 3 * H + jb;
         if (vec_ok) {
           if (b_ok) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(g)), r1 = __ldg(reinterpret_cast<const float4*>(g) + 1);
-            const float4 z0 = __ldg(reinterpret_cast<const float4*>(g + H)), z1 = __ldg(reinterpret_cast<const float4*>(g + H) + 1);
-            const float4 n0 = __ldg(reinterpret_cast<const float4*>(g + 2 * H)), n1 = __ldg(reinterpret_cast<const float4*>(g + 2 * H) + 1);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 r0 = q0_ok ? __ldg(reinterpret_cast<const float4*>(g)) : zero4;
+            const float4 r1 = q1_ok ? __ldg(reinterpret_cast<const float4*>(g) + 1) : zero4;
+            const float4 z0 = q0_ok ? __ldg(reinterpret_cast<const float4*>(g + H)) : zero4;
+            const float4 z1 = q1_ok ? __ldg(reinterpret_cast<const float4*>(g + H) + 1) : zero4;
+            const float4 n0 = q0_ok ? __ldg(reinterpret_cast<const float4*>(g + 2 * H)) : zero4;
+            const float4 n1 = q1_ok ? __ldg(reinterpret_cast<const float4*>(g + 2 * H) + 1) : zero4;
             gr[0] = r0.x; gr[1] = r0.y; gr[2] = r0.z; gr[3] = r0.w; gr[4] = r1.x; gr[5] = r1.y; gr[6] = r1.z; gr[7] = r1.w;
             gz[0] = z0.x; gz[1] = z0.y; gz[2] = z0.z; gz[3] = z0.w; gz[4] = z1.x; gz[5] = z1.y; gz[6] = z1.z; gz[7] = z1.w;
             gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
@@ -288,6 +297,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
           }
         }
       }
+      GRU_MARK(14);
       float ar[8], az[8], an[8];
       if (s > 0) {
         // fetch the operand image slice by slice as soon as each producer has published h_{s-1}: lanes 0..2 of every
@@ -298,13 +308,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
           if (lane < 3 && my_i < S) {
             const int sl = (my_i + slice) % S;
             unsigned spins = 0;
-            while (*reinterpret_cast<volatile unsigned*>(flags + sl * 32) < (unsigned)s) {
+            while (ld_acquire_u32(flags + sl * 32) < (unsigned)s) {
               if (++spins > (1u << 26)) __trap();
             }
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            GRU_MARK(12);
             GRU_MARK(1);
             if (dbg_cta) g_gru_slices[((s & 63) * 3 + 0) * MAX_SLICES + sl] = clock64();
             asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes (other SMs) -> async-proxy read
+            GRU_MARK(13);
             const unsigned char* src = img0 + (size_t)((s - 1) & 1) * 2 * a_half + (size_t)sl * 2 * PBM * 16;
             const uint32_t dst = smem_u32(a_hi) + (uint32_t)(sl * 2 * PBM * 16);
             const uint32_t bar = ready0 + 8 * sl;
@@ -323,11 +334,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
           }
           __syncwarp();
         }
+        if (p.dbg && group == 0 && s == 10 && tid == 0) g_gru_ctas[slice * 8 + 1] = gtimer();
         // layer output and saved gates of the PREVIOUS step: issued while the image is in flight
         store_prev();
+        if (p.dbg && group == 0 && s == 10 && tid == 0) g_gru_ctas[slice * 8 + 2] = gtimer();
         GRU_MARK(2);
         mbar_wait(mma_bar, (uint32_t)((s - 1) & 1));
         GRU_MARK(3);
+        if (p.dbg && group == 0 && s == 10 && tid == 0) g_gru_ctas[slice * 8 + 3] = gtimer();
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 8; ++i) ar[i] = az[i] = an[i] = 0.f;
@@ -376,14 +390,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
         GRU_MARK(5);
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 worker warps
         GRU_MARK(6);
-        if (tid == 0) st_release_u32(flags + slice * 32, (unsigned)(s + 1));  // release: cumulative over bar.sync
+        if (p.dbg && group == 0 && s == 10 && tid == 0) g_gru_ctas[slice * 8 + 4] = gtimer();
+        // release: cumulative over bar.sync.  (The gpu-scope fence costs ~1.3k cycles and stalls the memory
+        // instructions of every warp of the SM meanwhile -- measured; moving it to a helper warp gains nothing.)
+        if (tid == 0) st_release_u32(flags + slice * 32, (unsigned)(s + 1));
         GRU_MARK(7);
+        if (p.dbg && group == 0 && s == 10 && tid == 0) g_gru_ctas[slice * 8 + 5] = gtimer();
+        if (p.dbg && group == 0 && s == 9 && tid == 0) g_gru_ctas[slice * 8 + 0] = gtimer();
       }
       // layer output and saved gates: kept in registers, stored at the next step while its image is in flight
 #pragma unroll
       for (int i = 0; i < 8; ++i) { ph[i] = h_own[i]; pr[i] = rr[i]; pz[i] = zz[i]; pn[i] = nn[i]; pg[i] = gh[i]; }
       pt = t;
       if (s == 0 || s + 1 == T) store_prev();  // step 0 has no fetch phase; the last step has no successor
+      GRU_MARK(15);
     }
   }
   tc_fence_before();
@@ -464,12 +484,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
   const int wg = warp >> 2;
   const int u0 = wg * 8, jb = j0 + u0;
   const bool b_ok = b < B;
-  const bool vec_ok = (H & 3) == 0 && jb + 8 <= H && (p.lddout & 3) == 0 && ((p.dir_stride & 3) == 0) &&
+  const bool vec_ok = (H & 3) == 0 && (p.lddout & 3) == 0 && ((p.dir_stride & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.dout) | reinterpret_cast<uintptr_t>(p.out) |
                         reinterpret_cast<uintptr_t>(p.dgi) | reinterpret_cast<uintptr_t>(p.dgh)) & 15) == 0;
   // 32-byte stores of the dgi / dgh rows: every gate segment (3H*4, H*4, jb*4 bytes) must keep 32-byte alignment
   const bool vec32_ok = vec_ok && (H & 7) == 0 &&
                         ((reinterpret_cast<uintptr_t>(p.dgi) | reinterpret_cast<uintptr_t>(p.dgh)) & 31) == 0;
+  // the last slice may own a partial group of units: validity per 4 units (H % 4 == 0 on the vector paths)
+  const bool q0_ok = jb + 4 <= H, q1_ok = jb + 8 <= H;
   float carry[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) carry[i] = 0.f;
@@ -492,10 +514,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
     const float* dp = p.dout + rowi * p.lddout + (long)dir * p.dir_stride + jb;
     const float* hq = p.out + ((long)(b_ok ? b : 0) * T + (fs > 0 ? tprev : t)) * 2 * H + (long)dir * H + jb;
     if (vec_ok && b_ok) {
-      const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 d0 = q0_ok ? __ldg(reinterpret_cast<const float4*>(dp)) : zero4;
+      const float4 d1 = q1_ok ? __ldg(reinterpret_cast<const float4*>(dp) + 1) : zero4;
       ndh[0] = d0.x; ndh[1] = d0.y; ndh[2] = d0.z; ndh[3] = d0.w; ndh[4] = d1.x; ndh[5] = d1.y; ndh[6] = d1.z; ndh[7] = d1.w;
       if (fs > 0) {
-        const float4 h0 = __ldg(reinterpret_cast<const float4*>(hq)), h1 = __ldg(reinterpret_cast<const float4*>(hq) + 1);
+        const float4 h0 = q0_ok ? __ldg(reinterpret_cast<const float4*>(hq)) : zero4;
+        const float4 h1 = q1_ok ? __ldg(reinterpret_cast<const float4*>(hq) + 1) : zero4;
         nhp[0] = h0.x; nhp[1] = h0.y; nhp[2] = h0.z; nhp[3] = h0.w; nhp[4] = h1.x; nhp[5] = h1.y; nhp[6] = h1.z; nhp[7] = h1.w;
       } else {
 #pragma unroll
@@ -547,21 +572,20 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       if (!b_ok) return;
       float* a = p.dgi + (rowi * 2 + dir) * 3 * H + jb;
       float* c = p.dgh + (rowi * 2 + dir) * 3 * H + jb;
-      if (vec32_ok) {
-        st_global_v8(a, dr); st_global_v8(c, dr);
-        st_global_v8(a + H, dz); st_global_v8(c + H, dz);
-        st_global_v8(a + 2 * H, dn); st_global_v8(c + 2 * H, dnr);
+      if (vec32_ok) {  // H % 8 == 0: a group of 8 units is valid as a whole or not at all
+        if (q1_ok) {
+          st_global_v8(a, dr); st_global_v8(c, dr);
+          st_global_v8(a + H, dz); st_global_v8(c + H, dz);
+          st_global_v8(a + 2 * H, dn); st_global_v8(c + 2 * H, dnr);
+        }
       } else if (vec_ok) {
-        float4* a4; float4* c4;
-        a4 = reinterpret_cast<float4*>(a); c4 = reinterpret_cast<float4*>(c);
-        a4[0] = make_float4(dr[0], dr[1], dr[2], dr[3]); a4[1] = make_float4(dr[4], dr[5], dr[6], dr[7]);
-        c4[0] = a4[0]; c4[1] = a4[1];
-        a4 = reinterpret_cast<float4*>(a + H); c4 = reinterpret_cast<float4*>(c + H);
-        a4[0] = make_float4(dz[0], dz[1], dz[2], dz[3]); a4[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
-        c4[0] = a4[0]; c4[1] = a4[1];
-        a4 = reinterpret_cast<float4*>(a + 2 * H); c4 = reinterpret_cast<float4*>(c + 2 * H);
-        a4[0] = make_float4(dn[0], dn[1], dn[2], dn[3]); a4[1] = make_float4(dn[4], dn[5], dn[6], dn[7]);
-        c4[0] = make_float4(dnr[0], dnr[1], dnr[2], dnr[3]); c4[1] = make_float4(dnr[4], dnr[5], dnr[6], dnr[7]);
+        auto st2 = [&](float* dst, const float (&v)[8]) {
+          if (q0_ok) reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+          if (q1_ok) reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        };
+        st2(a, dr); st2(c, dr);
+        st2(a + H, dz); st2(c + H, dz);
+        st2(a + 2 * H, dn); st2(c + 2 * H, dnr);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -678,6 +702,9 @@ int gru_debug_read_timeline(long long* host, int n) {
   int n2 = n - n1;
   if (n2 > 64 * 3 * grup::MAX_SLICES) n2 = 64 * 3 * grup::MAX_SLICES;
   if (n2 > 0 && cudaMemcpyFromSymbol(host + n1, grup::g_gru_slices, sizeof(long long) * n2) != cudaSuccess) return -2;
+  int n3 = n - n1 - 64 * 3 * grup::MAX_SLICES;
+  if (n3 > grup::MAX_SLICES * 8) n3 = grup::MAX_SLICES * 8;
+  if (n3 > 0 && cudaMemcpyFromSymbol(host + n1 + 64 * 3 * grup::MAX_SLICES, grup::g_gru_ctas, sizeof(long long) * n3) != cudaSuccess) return -2;
   return 0;
 }
 

@@ -30,11 +30,11 @@ with torch.no_grad():
     torch.cuda.synchronize()
     lib.s2ag_debug_flags(0)
 NS = 24
-buf = (ctypes.c_longlong * (64 * 16 + 64 * 3 * NS))()
+buf = (ctypes.c_longlong * (64 * 16 + 64 * 3 * NS + NS * 8))()
 lib.s2ag_debug_read_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
-assert lib.s2ag_debug_read_timeline(buf, 64 * 16 + 64 * 3 * NS) == 0
+assert lib.s2ag_debug_read_timeline(buf, 64 * 16 + 64 * 3 * NS + NS * 8) == 0
 tl = [[buf[s * 16 + i] for i in range(16)] for s in range(T)]
-names = {0: "step start", 1: "first flag seen", 2: "copies issued", 3: "mma_bar done", 4: "tmem read", 5: "stores issued",
+names = {0: "step start", 14: "gi loads issued", 15: "loop end", 12: "flag seen (pre-fence)", 13: "after proxy fence", 1: "after acq_rel fence", 2: "copies issued", 3: "mma_bar done", 4: "tmem read", 5: "stores issued",
          6: "bar.sync done", 7: "flag released", 8: "[mma] tfree", 9: "[mma] ready[0]", 10: "[mma] ready[S-1]", 11: "[mma] committed"}
 print("B=%d H=%d: per-step marks relative to step start (cycles), steps 2..T-2 averaged" % (B, H))
 acc = {}
@@ -57,3 +57,10 @@ print("step %d per-slice (cycles after step start): flag seen / copy issued / la
 for sl in range(S):
     v = [buf[off + ((st * 3 + k) * NS) + sl] - base for k in range(3)]
     print("  slice %2d  %7d %7d %7d" % (sl, v[0], v[1], v[2]))
+
+o3 = 64 * 16 + 64 * 3 * NS
+t0 = min(buf[o3 + sl * 8 + 0] for sl in range(S))
+print("every slice CTA of group 0 (globaltimer ns after the earliest step-9 release): rel9 | step10: polled+issued, stores done, mma_bar, pre-release, released")
+for sl in range(S):
+    v = [buf[o3 + sl * 8 + k] - t0 for k in range(6)]
+    print("  slice %2d  %6d | %6d %6d %6d %6d %6d" % (sl, *v))
