@@ -12,6 +12,9 @@ namespace s2ag {
 bool conv_shift_launch(const float* x, long ldpix_x, int N, int H, int W, int Cin, const float* w, int w_mode, int w_ci,
                        const float* bias, float* y, long ldpix_y, int Cout, int KH, int KW, int ph, int pw, int Ho,
                        int Wo, int act, float slope, int accumulate, void* stream);
+// umma_wgrad.cu: their weight gradients (shifted-window contraction over pixels, accumulators resident in TMEM)
+bool conv_wgrad_shift_launch(const float* dy, long ldpix_dy, const float* x, long ldpix_x, int N, int H, int W, int Cin,
+                             float* dw, int Cout, int KH, int KW, int ph, int pw, int Ho, int Wo, void* stream);
 }
 #endif
 
@@ -300,6 +303,14 @@ extern "C" int s2ag_conv_bwd_weight(const float* dy, long ldpix_dy, const float*
   int Mrows = N * Ho * Wo;
   if (Mrows == 0) return S2AG_OK;
   int K = Cin * KH * KW;
+#ifndef S2AG_EMU
+  if (g_engine == 0 && sh == 1 && sw == 1 && dh == 1 && dwd == 1 &&
+      conv_wgrad_shift_launch(dy, ldpix_dy, x, ldpix_x, N, H, W, Cin, dw, Cout, KH, KW, ph, pw, Ho, Wo, stream)) {
+    if (db) launch_colsum(dy, ldpix_dy, db, Mrows, Cout, stream);
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
+#endif
   // dw[co, kcol] += sum_row dy[row, co] * im2col(x)[row, kcol]
   LdPlain<false> a{dy, 1, ldpix_dy, 0};
   // columns in (kh, kw, c) order (consecutive columns = contiguous channels of x); the epilogue stores column

@@ -3,6 +3,7 @@
 // for the tiny shapes (K < 32, N < 16, M < 64) and in the CPU logic-emulation build of tests/emu.
 // s2ag_set_engine(1) forces the SIMT kernel everywhere (A/B parity checks on the GPU).
 #pragma once
+#include <cstdio>
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
 
@@ -10,10 +11,8 @@ namespace s2ag {
 extern int g_engine;  // 0 = auto, 1 = SIMT only
 
 template <class LdA, class LdB, class Epi>
-static inline void launch_gemm(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
-                               void* stream) {
-  if (M <= 0 || N <= 0) return;
-  if (splitk < 1) splitk = 1;
+static inline void launch_gemm_untimed(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch,
+                                       int splitk, void* stream) {
 #ifndef S2AG_EMU
   if (g_engine == 0 && umma::worthwhile(M, N, K)) {
     umma::launch(a, b, epi, M, N, K, nbatch, splitk, stream);
@@ -21,5 +20,30 @@ static inline void launch_gemm(const LdA& a, const LdB& b, const Epi& epi, int M
   }
 #endif
   launch_gemm_simt(a, b, epi, M, N, K, nbatch, splitk, stream);
+}
+
+template <class LdA, class LdB, class Epi>
+static inline void launch_gemm(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch, int splitk,
+                               void* stream) {
+  if (M <= 0 || N <= 0) return;
+  if (splitk < 1) splitk = 1;
+#ifndef S2AG_EMU
+  if (umma::g_dbg_flags & 32) {
+    // bring-up aid (s2ag_debug_flags bit 5, eager mode only): one stderr line per contraction with its device time
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, (cudaStream_t)stream);
+    launch_gemm_untimed(a, b, epi, M, N, K, nbatch, splitk, stream);
+    cudaEventRecord(e1, (cudaStream_t)stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[gemm] %8.1f us  M=%d N=%d K=%d batch=%d splitk=%d  %6.1f TF/s  %s\n", ms * 1e3f, M, N, K, nbatch, splitk,
+            2.0 * M * N * (double)K * nbatch / (ms * 1e-3) * 1e-12, __PRETTY_FUNCTION__);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return;
+  }
+#endif
+  launch_gemm_untimed(a, b, epi, M, N, K, nbatch, splitk, stream);
 }
 }  // namespace s2ag

@@ -78,6 +78,18 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (the branch around it must be warp-uniform)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; bf16 inputs, fp32 accumulate, M=128, N and majors from idesc
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -210,9 +222,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(LdA a, LdB b, Epi
   const uint32_t idesc = make_idesc(BN);
   const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;
 
-  if (warp == STAGE_THREADS / 32) {
+  // (warp index through __shfl_sync so that the compiler can prove the branch warp-uniform: the descriptors of the
+  //  elected issuer thread then live in uniform registers; a `lane == 0` branch wraps every tcgen05.mma in an
+  //  elect / R2UR.BROADCAST waterfall loop)
+  if (__shfl_sync(0xffffffffu, warp, 0) == STAGE_THREADS / 32) {
     // ================= MMA issuer warp: one thread, decoupled from the staging warps by the full / empty mbarriers
-    if (lane == 0) {
+    if (elect_one()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int st_i = kb & 1;
         mbar_wait(bar_full[st_i], (uint32_t)((kb >> 1) & 1));

@@ -59,6 +59,7 @@ __device__ __forceinline__ void tmem_ld8c(uint32_t taddr, float (&r)[8]) {
 __global__ void __launch_bounds__(CTHREADS, 2) conv_shift_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: issuer descriptors in uniform registers
   const uint32_t sbase = smem_u32(smem);
   const uint32_t mma_bar = sbase;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 16);
@@ -142,9 +143,9 @@ __global__ void __launch_bounds__(CTHREADS, 2) conv_shift_kernel(Params p) {
       fence_async_smem();
     }
     __syncthreads();
-    if (warp >= 8 && lane == 0) {
+    if (warp_u >= 8 && elect_one()) {
       // ---- issuer `iss`: taps iss, iss + NISS, ... into accumulator iss
-      const int iss = warp - 8;
+      const int iss = warp_u - 8;
       tc_fence_after();
       const uint32_t idesc = make_idesc(Np);
       const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = (uint32_t)Np * 16;

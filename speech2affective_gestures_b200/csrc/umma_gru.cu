@@ -167,14 +167,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
   const uint32_t tmem_base = *tmem_slot;
 
   const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  if (warp >= 8) {
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: issuer descriptors in uniform registers
+  if (warp_u >= 8) {
     // ================================ MMA issuers ================================
     // One lane of each of the NISSUE issuer warps takes the k-steps kk = iss, iss + NISSUE, ... (a single thread
     // executes the ~dozens of dependent scalar instructions around each tcgen05.mma at only one every few cycles:
     // four issue streams keep the tail after the last slice short) and accumulates into its own two TMEM
     // accumulators; each issuer commits to mma_bar (NISSUE arrivals).
-    if (lane == 0) {
-      const int iss = warp - 8;
+    if (elect_one()) {
+      const int iss = warp_u - 8;
       const bool dbg = dbg_cta && iss == 0;
       const uint32_t idesc = make_idesc(NC);
       const uint32_t a_lbo = PBM * 16, w_lbo = NC * 16;
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
     *reinterpret_cast<uint4*>(w_lo + (kc * Kpad + n) * 16) = lo;
   }
 
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: issuer descriptors in uniform registers
   const int row = (warp & 3) * 32 + lane;
   const int b = bt * PBM + row;
   const int wg = warp >> 2;
@@ -615,10 +617,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) gru_persist_bwd_kernel(BwdParams 
       BWD_MARK(1);
       __syncthreads();
       BWD_MARK(2);
-      if ((tid == 0) || (tid == 32 && n2 > 0)) {
+      if ((warp_u == 0 || (warp_u == 1 && n2 > 0)) && elect_one()) {
         // one issuer thread per accumulator half: 9 dependent tcgen05.mma each instead of 18 in one stream
         tc_fence_after();
-        const int half = tid == 0 ? 0 : 1;
+        const int half = warp_u;
         const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
         const uint32_t a_lbo = PBM * 16, w_lbo = (uint32_t)Kpad * 16;
         const int nn = half == 0 ? n1 : n2;
