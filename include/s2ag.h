@@ -37,6 +37,10 @@ int s2ag_stream_capture_status(void* stream);
 /* Dense-contraction engine: 0 = auto (tcgen05 tensor-core kernel wherever a 128 x BN tile is worthwhile,
  * exact-fp32 SIMT kernel for tiny shapes), 1 = SIMT everywhere (A/B parity checks). */
 int s2ag_set_engine(int engine);
+/* Scratch for the tensor-core operand images of weight operands (gemm_umma_packed.cuh): a device buffer owned by the
+ * caller, registered for ONE stream (kernels of that stream use it in stream order).  Without a registered buffer
+ * that is large enough the contraction stages both operands on the fly.  (NULL, 0) unregisters. */
+int s2ag_register_scratch(void* stream, void* buf, long bytes);
 /* Tensor-core operand precision: 0 = "bf16x3" (fp32 operands split hi+lo on the fly, three MMAs, fp32
  * accumulate in TMEM: fp32-grade results, the default and the parity configuration), 1 = "bf16x1"
  * (single bf16 pass, BASELINE config 3). */

@@ -19,6 +19,29 @@ int g_engine = 0;
 namespace umma { int g_precision = 0; int g_dbg_flags = 0; }
 #endif
 }  // namespace s2ag
+// Scratch buffers are owned by the caller and registered per stream (no hidden allocation in the library).
+namespace s2ag {
+struct Scratch { void* stream; void* buf; long bytes; };
+static Scratch g_scratch[32];
+static int g_nscratch = 0;
+void* scratch_get(void* stream, long bytes) {
+  for (int i = 0; i < g_nscratch; ++i)
+    if (g_scratch[i].stream == stream) return (g_scratch[i].buf && g_scratch[i].bytes >= bytes) ? g_scratch[i].buf : nullptr;
+  return nullptr;
+}
+}  // namespace s2ag
+extern "C" int s2ag_register_scratch(void* stream, void* buf, long bytes) {
+  using namespace s2ag;
+  if ((buf == nullptr) != (bytes == 0) || bytes < 0 || (reinterpret_cast<unsigned long long>(buf) & 15ull)) {
+    s2ag_set_error("s2ag_register_scratch: need a 16-byte aligned buffer with bytes > 0, or (NULL, 0) to unregister");
+    return S2AG_ERR_ARG;
+  }
+  for (int i = 0; i < g_nscratch; ++i)
+    if (g_scratch[i].stream == stream) { g_scratch[i].buf = buf; g_scratch[i].bytes = bytes; return S2AG_OK; }
+  if (g_nscratch == 32) { s2ag_set_error("s2ag_register_scratch: more than 32 streams"); return S2AG_ERR_ARG; }
+  g_scratch[g_nscratch++] = Scratch{stream, buf, bytes};
+  return S2AG_OK;
+}
 extern "C" int s2ag_set_engine(int engine) {
   if (engine < 0 || engine > 1) { s2ag_set_error("s2ag_set_engine: engine must be 0 (auto) or 1 (SIMT)"); return S2AG_ERR_ARG; }
   s2ag::g_engine = engine;

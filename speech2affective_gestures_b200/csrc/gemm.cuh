@@ -6,15 +6,29 @@
 #include <cstdio>
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
+#include "gemm_umma_packed.cuh"
 
 namespace s2ag {
 extern int g_engine;  // 0 = auto, 1 = SIMT only
+void* scratch_get(void* stream, long bytes);  // capi.cu: scratch registered for `stream` if it holds >= bytes, else NULL
 
 template <class LdA, class LdB, class Epi>
 static inline void launch_gemm_untimed(const LdA& a, const LdB& b, const Epi& epi, int M, int N, int K, int nbatch,
                                        int splitk, void* stream) {
 #ifndef S2AG_EMU
   if (g_engine == 0 && umma::worthwhile(M, N, K)) {
+    // B reused by >= 4 row tiles (a weight, or any operand small next to A): pack it once into the tensor-core
+    // operand image and let the CTAs fetch it by TMA (gemm_umma_packed.cuh) -- needs a scratch buffer registered
+    // for this stream (s2ag_register_scratch); without one the on-the-fly kernel runs.
+    if (M >= 4 * umma::BM && !(umma::g_dbg_flags & 256)) {
+      const long bytes = umma::packed_bytes(N, K, nbatch);
+      void* img = scratch_get(stream, bytes);
+      if (img != nullptr) {
+        const umma::PackedB pb = umma::pack_operand(b, N, K, nbatch, img, stream);
+        umma::launch_packed(a, pb, epi, M, N, K, nbatch, splitk, stream);
+        return;
+      }
+    }
     umma::launch(a, b, epi, M, N, K, nbatch, splitk, stream);
     return;
   }
@@ -46,4 +60,5 @@ static inline void launch_gemm(const LdA& a, const LdB& b, const Epi& epi, int M
 #endif
   launch_gemm_untimed(a, b, epi, M, N, K, nbatch, splitk, stream);
 }
+
 }  // namespace s2ag

@@ -51,9 +51,26 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+# Scratch for the packed weight-operand images of the tcgen05 contractions (s2ag_register_scratch): one buffer per
+# stream that launches library kernels, owned here.  Never allocated while a CUDA graph is being captured (a stream
+# first seen during capture simply runs the contractions that stage both operands on the fly).
+SCRATCH_BYTES = 32 << 20
+_SCRATCH = {}
+
+
+def _handle(stream, device):
+    h = stream.cuda_stream
+    key = (device.index, h)
+    if key not in _SCRATCH and not torch.cuda.is_current_stream_capturing():
+        buf = torch.empty(SCRATCH_BYTES, dtype=torch.uint8, device=device)
+        _C.call("s2ag_register_scratch", ctypes.c_void_p(h), ctypes.c_void_p(buf.data_ptr()), SCRATCH_BYTES)
+        _SCRATCH[key] = buf
+    return ctypes.c_void_p(h)
+
+
 def _stream(t):
     if t.is_cuda:
-        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        return _handle(torch.cuda.current_stream(t.device), t.device)
     return None
 
 
@@ -609,7 +626,7 @@ class BiGruFn(torch.autograd.Function):
                 ev.record(main)
                 side.wait_event(ev)
                 _C.call("s2ag_gru_layer_bwd", *args, _p(wsl), B, T, rec["In"], H, 4,
-                        ctypes.c_void_p(side.cuda_stream))
+                        _handle(side, dy.device))
                 for t_ in (wsl, rec["x"], rec["out"], rec["gates"], d):
                     if t_ is not None:
                         t_.record_stream(side)
