@@ -270,8 +270,9 @@ class _SpeakerMixin:
                 self.speaker_mu = nn.Linear(self.z_size, self.z_size)
                 self.speaker_log_var = nn.Linear(self.z_size, self.z_size)
 
-    def _speaker_z(self, in_text, vid_indices, buf, off):
-        """-> (z_context, z_mu, z_log_var, tiled-slice-or-None); writes z tiled over T into buf[:, :, off:]"""
+    def _speaker_z(self, in_text, vid_indices, buf, off, eps=None):
+        """-> (z_context, z_mu, z_log_var, tiled-slice-or-None); writes z tiled over T into buf[:, :, off:].
+        eps: re-parametrisation noise drawn by the caller (to fix the order of the draws), else drawn here."""
         if not self.z_obj:
             return None, None, None, None
         if self.speaker_embedding:
@@ -280,7 +281,7 @@ class _SpeakerMixin:
             zc = ops.linear(e, self.speaker_embedding[1].weight, self.speaker_embedding[1].bias)
             z_mu = ops.linear(zc, self.speaker_mu.weight, self.speaker_mu.bias)
             z_log_var = ops.linear(zc, self.speaker_log_var.weight, self.speaker_log_var.bias)
-            z, tiled = ops.reparam_tile(z_mu, z_log_var, en.draw_eps(z_mu), buf, off)
+            z, tiled = ops.reparam_tile(z_mu, z_log_var, eps if eps is not None else en.draw_eps(z_mu), buf, off)
             return z, z_mu, z_log_var, tiled
         # random-noise style vector (:519-520): mu = 0, log_var = 0, eps = randn
         zeros = torch.zeros(in_text.shape[0], self.z_size, device=buf.device)
@@ -416,7 +417,7 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
         weights, so a driver may evaluate it on a side stream while the recurrent kernels of another pass run."""
         return self.text_encoder(in_text)[0]
 
-    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None, shared=None, text_feat=None):
+    def forward(self, pre_seq, in_text, in_mfcc, vid_indices=None, shared=None, text_feat=None, eps=None):
         B, T = pre_seq.shape[0], pre_seq.shape[1]
         buf = torch.empty(B, T, self.in_size, dtype=torch.float32, device=pre_seq.device)
         pieces, slices = [], []
@@ -445,7 +446,7 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
                     'Audio and text features must have the same number of time steps. ' \
                     'Found time steps: audio features: {}, text features: {}.'.format(a.shape[1], t.shape[1])
             pieces.append(t); slices.append((col, col + 32)); col += 32
-        z, z_mu, z_log_var, tiled = self._speaker_z(in_text, vid_indices, buf, col)
+        z, z_mu, z_log_var, tiled = self._speaker_z(in_text, vid_indices, buf, col, eps=eps)
         if tiled is not None and tiled.requires_grad:
             pieces.append(tiled); slices.append((col, col + self.z_size))
         g = ops.bigru(buf, _gru_param_list(self.gru), self.gru.num_layers, self.hidden_size, self.gru.dropout,

@@ -192,6 +192,7 @@ class Processor(object):
         use_side = self.device.type == "cuda" and self.use_side_stream
         main_s = torch.cuda.current_stream() if use_side else None
         txt1 = txt2 = txt3 = tri_pre = None
+        eps2 = eps3 = early3 = None
         ev = {}
         if use_side:
             if self._side_stream is None:
@@ -247,6 +248,31 @@ class Processor(object):
                     if t_ is not None:
                         t_.record_stream(sb)
                 pre_seq.record_stream(sb)
+                if use_div and train:
+                    # Generator pass #3 (the no-grad style-diversity pass, :903-910) depends on nothing the D step or
+                    # pass #2 produce: it follows the baseline on the same side stream, still beside the D step.  The
+                    # re-parametrisation noise of passes #2 and #3 is drawn here, in the reference's order.
+                    if cfg.z_type == 'speaker':
+                        like = torch.empty(vid_indices.shape[0], G.z_size, device=self.device)
+                        eps2, eps3 = en.draw_eps(like), en.draw_eps(like)
+                        rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
+                            torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
+                        rand_vids = vid_indices[rand_idx]
+                    else:
+                        rand_vids = None
+                    ev_r = torch.cuda.Event(); ev_r.record(main_s)
+                    sb.wait_event(ev_r)
+                    sb.wait_event(ev[3])
+                    with torch.cuda.stream(sb):
+                        with torch.no_grad():
+                            early3 = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng, text_feat=txt3, eps=eps3)
+                    ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
+                    for t_ in shared_ng + (txt3, rand_vids, eps3, in_text, in_mfcc):
+                        if t_ is not None:
+                            t_.record_stream(sb)
+                    for t_ in early3:
+                        if t_ is not None:
+                            t_.record_stream(main_s)
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
@@ -271,7 +297,7 @@ class Processor(object):
         if use_side:
             main_s.wait_event(ev[2])
         with torch.set_grad_enabled(train):
-            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2)
+            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2, eps=eps2)
             # D's own parameter gradients from this pass are discarded by the reference (zero_grad at the
             # next D step, :794), so they are not computed; gradients still flow through D into G.
             d_params = [p for p in D.parameters() if p.requires_grad]
@@ -283,7 +309,9 @@ class Processor(object):
                 for p in d_params:
                     p.requires_grad_(True)
         out_rand = z_rand = None
-        if use_div:
+        if early3 is not None:
+            out_rand, z_rand = early3[0], early3[1]
+        elif use_div:
             if cfg.z_type == 'speaker':
                 # torch.randperm(B) of processor_v2.py:903; drawn as argsort(uniform) on the device so that
                 # the draw is capturable in a CUDA graph (CUDA randperm synchronises the host)
