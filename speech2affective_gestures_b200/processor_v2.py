@@ -192,7 +192,7 @@ class Processor(object):
         use_side = self.device.type == "cuda" and self.use_side_stream
         main_s = torch.cuda.current_stream() if use_side else None
         txt1 = txt2 = txt3 = tri_pre = None
-        eps2 = eps3 = early3 = None
+        eps2 = eps3 = early3 = early2 = None
         ev = {}
         if use_side:
             if self._side_stream is None:
@@ -273,6 +273,22 @@ class Processor(object):
                     for t_ in early3:
                         if t_ is not None:
                             t_.record_stream(main_s)
+                if train:
+                    # Generator pass #2 (the forward of the G step, :823) does not depend on the D update either (only
+                    # D(out) after it does): it follows on the same side stream, so the G step on the main stream starts
+                    # at D(out).  autograd runs its backward (BPTT) on this stream and orders it against the rest.
+                    sb.wait_event(ev[2])
+                    ev_m = torch.cuda.Event(); ev_m.record(main_s)
+                    sb.wait_event(ev_m)
+                    with torch.cuda.stream(sb):
+                        early2 = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2, eps=eps2)
+                    ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
+                    for t_ in tuple(shared) + (txt2, vid_indices, eps2, in_text, in_mfcc):
+                        if t_ is not None:
+                            t_.record_stream(sb)
+                    for t_ in early2:
+                        if t_ is not None:
+                            t_.record_stream(main_s)
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
@@ -297,7 +313,11 @@ class Processor(object):
         if use_side:
             main_s.wait_event(ev[2])
         with torch.set_grad_enabled(train):
-            out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2, eps=eps2)
+            if early2 is not None:
+                out, z, z_mu, z_log_var = early2
+            else:
+                out, z, z_mu, z_log_var = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2,
+                                            eps=eps2)
             # D's own parameter gradients from this pass are discarded by the reference (zero_grad at the
             # next D step, :794), so they are not computed; gradients still flow through D into G.
             d_params = [p for p in D.parameters() if p.requires_grad]
@@ -339,8 +359,11 @@ class Processor(object):
                 outs += [z_mu, z_log_var]; grads += [g_mu, g_lv]
             torch.autograd.backward(outs, grads)
             if use_side:
-                # the text-encoder backward (and its in-kernel parameter-gradient accumulation) ran on the side stream
+                # the text-encoder backward (and its in-kernel parameter-gradient accumulation) ran on the side stream,
+                # the generator's own backward on the second one
                 main_s.wait_stream(self._side_stream)
+                if self._side_stream_b is not None:
+                    main_s.wait_stream(self._side_stream_b)
             self._allreduce_grads(G)
             ops.adam_step(G.flat_params, G.flat_grads, self.gen_m, self.gen_v, self.lr_s2ag_gen, 0.5, 0.999, 1e-8,
                           self.gen_step, 1.0 / self.world)
