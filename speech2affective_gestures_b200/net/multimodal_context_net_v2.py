@@ -328,7 +328,7 @@ class PoseGeneratorTriModal(FlatParamNet, _SpeakerMixin):
         t = self.text_encoder(in_text)[0] if self.input_context in ('both', 'text') else None
         return a, t
 
-    def forward(self, pre_seq, in_text, in_audio, vid_indices=None, pre=None):
+    def forward(self, pre_seq, in_text, in_audio, vid_indices=None, pre=None, eps=None):
         B, T = pre_seq.shape[0], pre_seq.shape[1]
         buf = torch.empty(B, T, self.in_size, dtype=torch.float32, device=pre_seq.device)
         pieces, slices = [], []
@@ -352,7 +352,7 @@ class PoseGeneratorTriModal(FlatParamNet, _SpeakerMixin):
             if self.input_context == 'both':
                 assert a.shape[1] == t.shape[1]
             pieces.append(t); slices.append((col, col + 32)); col += 32
-        z, z_mu, z_log_var, tiled = self._speaker_z(in_text, vid_indices, buf, col)
+        z, z_mu, z_log_var, tiled = self._speaker_z(in_text, vid_indices, buf, col, eps=eps)
         if tiled is not None and tiled.requires_grad:
             pieces.append(tiled); slices.append((col, col + self.z_size))
         g = ops.bigru(buf, _gru_param_list(self.gru), self.gru.num_layers, self.hidden_size, self.gru.dropout,

@@ -239,14 +239,25 @@ class Processor(object):
                 ev_p1 = torch.cuda.Event(); ev_p1.record(main_s)
                 sb.wait_event(ev_p1)
                 sb.wait_event(ev['t'])
-                with torch.cuda.stream(sb):
-                    with torch.no_grad():
-                        out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
-                ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
-                out_tri.record_stream(main_s)
-                for t_ in tri_pre:
-                    if t_ is not None:
-                        t_.record_stream(sb)
+                # (the baseline's re-parametrisation noise is drawn here, at its place in the reference's order)
+                eps_t = None
+                if getattr(Tri, 'speaker_embedding', None) is not None:
+                    eps_t = en.draw_eps(torch.empty(vid_indices.shape[0], Tri.z_size, device=self.device))
+
+                def run_tri():
+                    with torch.cuda.stream(sb):
+                        with torch.no_grad():
+                            o, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre, eps=eps_t)
+                    o.record_stream(main_s)
+                    for t_ in tuple(tri_pre) + (eps_t, in_text, in_audio, vid_indices):
+                        if t_ is not None:
+                            t_.record_stream(sb)
+                    return o
+
+                tri_late = train  # training: generator passes #3 / #2 first, the baseline beside D(out) (below)
+                if not tri_late:
+                    out_tri = run_tri()
+                    ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
                 pre_seq.record_stream(sb)
                 if use_div and train:
                     # Generator pass #3 (the no-grad style-diversity pass, :903-910) depends on nothing the D step or
@@ -289,6 +300,12 @@ class Processor(object):
                     for t_ in early2:
                         if t_ is not None:
                             t_.record_stream(main_s)
+                if tri_late:
+                    # The frozen baseline last: its generator-sized recurrent kernels then run beside the D(out) chain
+                    # of the G step (discriminator-sized kernels); its output is only needed by the final metric.  The
+                    # main stream joins this stream before the end of the step, and the generator's BPTT kernels are
+                    # queued behind it on this same stream.
+                    out_tri = run_tri()
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
