@@ -95,14 +95,15 @@ def run_reference_arm(args):
 
 
 # ncu --set full capture of the roofline launch (profiles/r01_ncu_umma_gemm.txt): dram__bytes_read.sum + dram__bytes_write.sum
-ROOFLINE_TRAFFIC_BYTES = 37511680  # 25.29 MB read + 12.22 MB written (final r01 capture)
+ROOFLINE_TRAFFIC_BYTES = 38848512  # 25.33 MB read + 13.52 MB written (profiles/r01_ncu_gemm_umma_pk.txt)
 
 
 def roofline(B, dev, lib, clips_per_s_per_gpu=None):
-    """The dense-contraction engine (gemm_umma_kernel, tcgen05) carries ~45 % of the step's device time; its largest
-    single shape is the GRU layer input projection [B*34, 600] x [600, 2*900] (both directions).  achieved =
-    algorithmic 2*M*N*K / CUDA-event time of that launch; the kernel issues 3 bf16 MMAs per algorithmic MAC in the
-    fp32-grade bf16x3 mode, so its tensor-pipe ceiling is 1/3 of the bf16 peak it is reported against."""
+    """The dense-contraction engine (gemm_umma_pk_kernel / gemm_umma_kernel, tcgen05) carries ~33 % of the step's kernel
+    time; its largest single shape is the GRU layer input projection [B*34, 600] x [600, 2*900] (both directions).
+    achieved = algorithmic 2*M*N*K / CUDA-event time of that call (weight packing + contraction); the kernel issues 3
+    bf16 MMAs per algorithmic MAC in the fp32-grade bf16x3 mode, so its tensor-pipe ceiling is 1/3 of the bf16 peak it is
+    reported against."""
     import torch
     from speech2affective_gestures_b200 import _C, ops
     pk = peaks()
@@ -124,8 +125,10 @@ def roofline(B, dev, lib, clips_per_s_per_gpu=None):
         tot += k0.elapsed_time(k1)
     kms = tot / reps
     ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
-    r = {"bound": "tensor", "kernel": "gemm_umma_kernel<LdPlain,LdPlain,EpiGeneric> (tcgen05; GRU input projection "
-                                      "%dx%dx%d, fp32 operands split bf16 hi/lo on the fly)" % (M, N, K),
+    r = {"bound": "tensor", "kernel": "gemm_umma_pk_kernel<LdPlain,EpiGeneric> (tcgen05; GRU input projection %dx%dx%d; "
+                                      "weight operand packed to bf16 hi/lo images once per call (pack_operand_kernel, "
+                                      "inside the timed call) and fetched by TMA, activation operand split on the fly)"
+                                      % (M, N, K),
          "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
          "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": pk["source"] + " (MEASURED_PEAKS.json bf16_tflops, burst)",
          "kernel_ms": kms, "algorithmic_flops": 2.0 * M * N * K,

@@ -58,6 +58,16 @@ for t, d in pts:
     last = t
     cur += d
 print("time with n kernels in flight: " + ", ".join("%d: %.0f us" % (n, v) for n, v in sorted(hist.items())))
+agg = collections.defaultdict(lambda: [0, 0.0])
+for s_, e_, name, _ in ks:
+    k = name.split("(")[0]
+    k = k[:k.index("<")] if "<" in k and not k.startswith("void at::") else k[:60]
+    agg[k][0] += 1
+    agg[k][1] += e_ - s_
+tot_k = sum(v[1] for v in agg.values())
+print("kernel time summed over streams %.1f us (%.2fx the span)" % (tot_k, tot_k / (t1 - t0)))
+for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+    print("  %5d  %9.1f us  %5.1f%%  %s" % (n, us, 100 * us / tot_k, k[-70:]))
 # coarse phases: every 0.5 ms, which kernels dominate
 bins = collections.defaultdict(lambda: collections.Counter())
 W = 500.0
