@@ -47,6 +47,13 @@ def test_library_exports_every_declared_symbol():
     cdll.s2ag_last_error.restype = ctypes.c_char_p
     assert cdll.s2ag_set_engine(7) < 0 and b"engine" in cdll.s2ag_last_error()
     assert cdll.s2ag_set_engine(0) == 0
+    # scratch registration is host-side bookkeeping: (stream, 16-byte aligned buffer, bytes) or (stream, NULL, 0)
+    cdll.s2ag_register_scratch.restype = ctypes.c_int
+    cdll.s2ag_register_scratch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    assert cdll.s2ag_register_scratch(ctypes.c_void_p(0x10), ctypes.c_void_p(0x1000), 4096) == 0
+    assert cdll.s2ag_register_scratch(ctypes.c_void_p(0x10), ctypes.c_void_p(0x1008), 4096) < 0   # misaligned
+    assert cdll.s2ag_register_scratch(ctypes.c_void_p(0x10), None, 4096) < 0                      # NULL with a size
+    assert cdll.s2ag_register_scratch(ctypes.c_void_p(0x10), None, 0) == 0                         # unregister
 
 
 def test_library_contains_sm100a_tensor_core_code():
