@@ -109,3 +109,31 @@ def test_conv_wgrad_shift_kernel(N, H, W, Cin, Cout, KH, KW, ph, pw):
     assert _rel(dw_simt, ref) < 1e-5
     assert _rel(dw_shift, ref) < 2e-5, _rel(dw_shift, ref)
     assert _rel(db_shift, dy.double().sum((0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("In,H,B", [(8, 64, 200), (24, 40, 5)])
+def test_cta_local_gru_experiment_matches_slice_parallel_kernels(In, H, B):
+    """umma_gru_local.cu (opt-in, s2ag_debug_flags bit 9; measured slower, see its header): same results as the
+    default slice-parallel persistent kernels, forward output and every gradient."""
+    dev = torch.device("cuda:0")
+    lib = _C.lib()
+    T, L = 34, 2
+    g = torch.Generator().manual_seed(In + H)
+    ps0 = [torch.randn(s, generator=g) * 0.2 for l in range(L) for s in
+           [(3 * H, In if l == 0 else 2 * H), (3 * H, H), (3 * H,), (3 * H,)] * 2]
+    x0 = torch.randn(B, T, In, generator=g)
+    gy = torch.randn(B, T, 2 * H, generator=g).to(dev)
+    res = {}
+    for name, flags in (("slices", 0), ("local", 512)):
+        lib.s2ag_debug_flags(flags)
+        try:
+            ps = [t.clone().to(dev).requires_grad_(True) for t in ps0]
+            x = x0.clone().to(dev).requires_grad_(True)
+            y = ops.bigru(x, ps, L, H, 0.0, False)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            res[name] = [y.detach(), x.grad] + [q.grad for q in ps]
+        finally:
+            lib.s2ag_debug_flags(0)
+    for a, b in zip(res["local"], res["slices"]):
+        assert _rel(a, b) < 2e-5, _rel(a, b)
