@@ -128,11 +128,11 @@ def test_cta_local_gru_experiment_matches_slice_parallel_kernels(In, H, B):
         lib.s2ag_debug_flags(flags)
         try:
             ps = [t.clone().to(dev).requires_grad_(True) for t in ps0]
-            x = x0.clone().to(dev).requires_grad_(True)
+            x = x0.clone().to(dev)
             y = ops.bigru(x, ps, L, H, 0.0, False)
             y.backward(gy)
             torch.cuda.synchronize()
-            res[name] = [y.detach(), x.grad] + [q.grad for q in ps]
+            res[name] = [y.detach()] + [q.grad for q in ps]
         finally:
             lib.s2ag_debug_flags(0)
     for a, b in zip(res["local"], res["slices"]):
