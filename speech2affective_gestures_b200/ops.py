@@ -385,8 +385,20 @@ class ConvBnActFn(torch.autograd.Function):
         w, b = ctx.w, ctx.b
         if w.requires_grad:
             db = _grad_of(b) if (b is not None and b.requires_grad) else None
+            side = _side_stream[0]
+            cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
+            wst = st
+            if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:
+                # the weight gradient is a leaf of the backward graph: it runs on the side stream beside the
+                # data-gradient chain (the caller joins the side stream before it consumes parameter gradients)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                wst = _handle(side, dy.device)
+                for t_ in (dc, ctx.x2):
+                    t_.record_stream(side)
             _C.call("s2ag_conv_bwd_weight", _p(dc), lddc, _p(ctx.x2), ldx, N, H, W, Cin, _p(_grad_of(w)), _p(db), Cout,
-                    KH, KW, sh, sw, ph, pw, dh, dw, st)
+                    KH, KW, sh, sw, ph, pw, dh, dw, wst)
         dx = None
         if ctx.needs_input_grad[0]:
             if sh != 1 or sw != 1:
