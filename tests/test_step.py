@@ -145,3 +145,48 @@ def test_eval_step_and_dropout_train_step(dev):
     ret = pr.forward_pass_s2ag(*dbatch[:3], dbatch[3], dbatch[4], train=True)[0]
     assert np.isfinite(ret) and all(np.isfinite(pr.metrics.tolist()))
     assert not torch.equal(before, pr.s2ag_generator.flat_params)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager_step():
+    """The benchmarked path is a CUDA-graph replay of the whole iteration (three streams, events, autograd across
+    streams).  From an identical state (weights, Adam moments, step counters, BatchNorm buffers, injected noise) the
+    replay must produce the same metrics, poses and updated weights as the eager call the parity tests exercise."""
+    dev = torch.device("cuda:0")
+    B, n_words, n_spk = 16, 200, 30
+    pr, c = make_processor("full", n_words, n_spk, dev, batch_size=B)
+    batch, eps_list, rand_idx = O.synthetic_batch(B, n_words, n_spk, 36267, 2024)
+    dbatch = tuple(x.to(dev) for x in batch)
+    pr.injected_rand_idx = rand_idx.to(dev)
+    for n in (pr.s2ag_generator, pr.s2ag_discriminator, pr.trimodal_generator):
+        n.train()
+    st = inject_eps([e.to(dev) for e in eps_list])   # device tensors: no host copy inside the capture
+    try:
+        # one eager pass first (registers the per-stream scratch, creates the side streams), then capture
+        pr.gan_step_async(dbatch[0], dbatch[1], dbatch[2], dbatch[3], dbatch[4], True)
+        torch.cuda.synchronize()
+        i0 = st["i"]
+        pr.capture_step(B, train=True, warmup=0)
+        nets = (pr.s2ag_generator, pr.s2ag_discriminator, pr.trimodal_generator)
+        state = [t for n in nets for t in n.state_dict().values()] + \
+                [pr.gen_m, pr.gen_v, pr.dis_m, pr.dis_v, pr.gen_step, pr.dis_step]
+        saved = [t.clone() for t in state]
+        pr.load_static_inputs(*dbatch)
+        pr.replay_step()
+        torch.cuda.synchronize()
+        m_graph, out_graph = pr.metrics.clone(), pr.last_out.clone()
+        w_graph = pr.s2ag_generator.flat_params.clone()
+        for t, s_ in zip(state, saved):
+            t.copy_(s_)
+        st["i"] = i0
+        pr.gan_step_async(*dbatch, True)
+        torch.cuda.synchronize()
+        assert torch.allclose(pr.metrics, m_graph, rtol=1e-5, atol=1e-7), (pr.metrics, m_graph)
+        assert rel(out_graph, pr.last_out) < 1e-5
+        # updated weights: Adam turns a rounding-level difference of a ~zero gradient (atomic summation order) into
+        # up to +-lr, so compare the bulk tightly and bound the rest
+        d = (w_graph - pr.s2ag_generator.flat_params).abs()
+        assert d.max().item() <= 2.5 * c["learning_rate"] + 1e-6
+        assert (d > 1e-6).float().mean().item() < 0.01
+    finally:
+        pr.injected_rand_idx = None
