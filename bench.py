@@ -285,11 +285,23 @@ def main():
     # ---- end-to-end timing (pinned host inputs -> H2D -> step -> D2H metrics), public Processor API
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pr.load_static_inputs(*host)
-        one_step()
-        host_metrics.copy_(pr.metrics, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    if use_graph:
+        # the loader's prefetch: the H2D copy of batch i+1 (copy stream, pinned memory) overlaps step i; every step's
+        # inputs cross PCIe once inside the timed region, the first copy is exposed
+        pr.prefetch_inputs(*host)
+        for i in range(args.steps):
+            pr.swap_in_prefetched()
+            if i + 1 < args.steps:
+                pr.prefetch_inputs(*host)
+            one_step()
+            host_metrics.copy_(pr.metrics, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    else:
+        for _ in range(args.steps):
+            pr.load_static_inputs(*host)
+            one_step()
+            host_metrics.copy_(pr.metrics, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
     t_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
     clk = clocks.stop() if rank == 0 else None
