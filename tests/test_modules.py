@@ -159,3 +159,21 @@ def test_no_cpu_fallback():
             ops._check(torch.zeros(2))
     finally:
         _C._emulated = was
+
+
+def test_explicit_eps_argument_equals_injected_draw(dev):
+    """The processor draws the re-parametrisation noise of the generator passes up front (reference order) and hands
+    it to forward(eps=...), so that the passes can be re-scheduled across streams: same result as drawing inside."""
+    G, T, D, C = build_nets("tiny", N_WORDS, N_SPK, dev)
+    text, audio, mfcc, target, vid, pre, eps_list, _ = _batch(3)
+    t = lambda a: a.to(dev)
+    for net, third in ((G, mfcc), (T, audio)):
+        net.eval()
+        with torch.no_grad():
+            inject_eps([eps_list[0]])
+            a = net(t(pre), t(text), t(third), t(vid))
+            st = inject_eps([eps_list[1]])           # must NOT be consumed when eps is passed explicitly
+            b = net(t(pre), t(text), t(third), t(vid), eps=t(eps_list[0]))
+        assert st["i"] == 0
+        for x, y in zip(a, b):
+            assert rel(x, y) < 1e-6
