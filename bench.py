@@ -70,6 +70,13 @@ def cpu_reference_clips_per_s(sample_b, steps, warmup, threads):
     return sample_b / dt, dt
 
 
+def workload_text(B):
+    """the same workload description on both arms"""
+    return ("full GAN step (D step + G step: 3 G fwd, 1 frozen tri-modal fwd incl. WavEncoder, 3 D fwd, G+D bwd, 2 Adam), "
+            "%d clips/GPU, 34 frames x 27-D, audio %d samples, 10-token text, n_words=%d, dropout as shipped"
+            % (B, AUDIO_LEN, N_WORDS))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -83,8 +90,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step",
         "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full GAN step (D+G fwd/bwd+Adam), %d clips/GPU, fp32, n_words=%d" % (
-            args.batch_per_gpu, N_WORDS)},
+        "config": {"workload": workload_text(args.batch_per_gpu),
+                   "sample": "bounded sample of that workload: %d clips per timed iteration, dropout off" % sample_b},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                          "sample": "%d timed GAN iterations of %d clips (oracle port of processor_v2.forward_pass_s2ag, "
                                    "dropout off)" % (steps, sample_b)},
@@ -330,9 +337,7 @@ def main():
             "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "bf16x3" else "bf16", "data": "synthetic",
-            "config": {"workload": "full GAN step (D step + G step: 3 G fwd, 1 frozen tri-modal fwd incl. WavEncoder, "
-                                   "3 D fwd, G+D bwd, 2 Adam), %d clips/GPU, 34 frames x 27-D, audio %d samples, "
-                                   "10-token text, n_words=%d, dropout as shipped" % (B, AUDIO_LEN, N_WORDS),
+            "config": {"workload": workload_text(B),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "precision": "%s (fp32 storage and accumulation; tensor-core operands %s)" % (
                            args.precision, "split bf16 hi+lo, 3 MMAs" if args.precision == "bf16x3" else "single bf16"),
