@@ -45,7 +45,16 @@ int s2ag_register_scratch(void* stream, void* buf, long bytes);
  * accumulate in TMEM: fp32-grade results, the default and the parity configuration), 1 = "bf16x1"
  * (single bf16 pass, BASELINE config 3). */
 int s2ag_set_precision(int mode);
-/* reserved for bring-up experiments of the tcgen05 kernels */
+/* Bring-up / A-B switches of the tcgen05 kernels (0 = production behaviour).  Bits:
+ *   2   clock64 / globaltimer timeline of the persistent GRU forward (s2ag_debug_read_timeline)
+ *   4   stride-1 convolutions and their weight gradients through the implicit-GEMM engine (no shifted-window kernels)
+ *   8   timeline of the persistent BPTT kernel
+ *   16  no FAST (LDG.256, unguarded) operand-load variant of the contraction kernels
+ *   32  one stderr line per dense contraction with its device time (eager mode only; synchronises)
+ *   64  conv_wgrad_shift_kernel skips its red.global epilogue (timing experiment; results are wrong)
+ *   128 conv_wgrad_shift_kernel wherever it is structurally applicable (default: only where it was measured faster)
+ *   256 no packed-weight route: both operands of every contraction are converted on the fly
+ *   512 CTA-local GRU kernels for H <= 64 (umma_gru_local.cu; measured slower, off by default) */
 int s2ag_debug_flags(int flags);
 /* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
  * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */
