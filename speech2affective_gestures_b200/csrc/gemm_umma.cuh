@@ -16,8 +16,10 @@
 //     no-swizzle K-major UMMA layout [k-chunk of 8][row][16 B], two stages; each warp fences
 //     (fence.proxy.async) and arrives on the stage's "full" mbarrier;
 //   - a 17th warp's elected thread waits for "full", issues the tcgen05.mma instructions of the stage
-//     (M=128, N=BN, K=16 each; a thread issues only about one tcgen05.mma per 160 cycles, so the issue
-//     must not sit on the staging warps' path) and tcgen05.commit's the stage's "empty" mbarrier: the
+//     (M=128, N=BN, K=16 each; the issuer branch is warp-uniform -- __shfl_sync'ed warp index + elect.sync -- so
+//     that the descriptors live in uniform registers and UTCHMMAs issue back to back; under a `lane == 0` branch
+//     the compiler wraps every tcgen05.mma in an elect / R2UR.BROADCAST loop of ~160 cycles) and
+//     tcgen05.commit's the stage's "empty" mbarrier: the
 //     tensor core works on stage s while the warps stage s^1, with no block-wide barrier in the loop;
 //   - accumulator: BN fp32 columns x 128 lanes of TMEM; epilogue: tcgen05.ld (32 lanes x 32
 //     columns per warp), transposed through shared memory so that global stores (and the

@@ -10,8 +10,8 @@
 //   * tap t is then one tcgen05.mma per 16 input channels whose A descriptor simply starts `shift(t)` rows further down
 //     the same image; B = that tap's [Cout x Cin] weight slab, stationary in shared memory for the CTA's lifetime
 //     (persistent CTAs loop over tiles);
-//   * four issuer threads take the taps round-robin into four TMEM accumulators that the epilogue sums (one thread
-//     issues only ~one tcgen05.mma per 160 cycles); anchors in the padding (hp >= Ho or wp >= Wo) are discarded.
+//   * four issuer threads (elected lanes of warp-uniform branches) take the taps round-robin into four TMEM
+//     accumulators that the epilogue sums; anchors in the padding (hp >= Ho or wp >= Wo) are discarded.
 // Data-gradient = the same kernel over dY with flipped taps, padding (K-1-p) and the transposed weight view.
 #include "s2ag.h"
 #include "gemm_umma.cuh"

@@ -97,9 +97,8 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
 // that slice has landed, so only the LAST slice to arrive is on the critical path of a time step.
 // 8 worker warps + 4 MMA-issuer warps
 constexpr int FWD_THREADS = 384, FWD_HDR = 512, MAX_SLICES = 24, NISSUE = 4;
-// Back-to-back tcgen05.mma into ONE accumulator serialise on the MMA latency (~160 cycles each for these tiny N=48
-// tiles, measured): the k-steps of a time step are spread round-robin over NACC independent TMEM accumulators that
-// the epilogue sums.
+// The k-steps of a time step are spread round-robin over NACC independent TMEM accumulators (two per issuer thread)
+// that the epilogue sums, so that the MMAs of a slice never wait for the accumulator of another one.
 constexpr int NACC = 8;  // = 2 per MMA-issuer thread
 
 // bring-up aid (s2ag_debug_flags bit 1): clock64 timeline of CTA (slice 0, tile 0, direction 0), 16 marks per step
@@ -170,10 +169,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gru_persist_fwd_kernel(Params 
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: issuer descriptors in uniform registers
   if (warp_u >= 8) {
     // ================================ MMA issuers ================================
-    // One lane of each of the NISSUE issuer warps takes the k-steps kk = iss, iss + NISSUE, ... (a single thread
-    // executes the ~dozens of dependent scalar instructions around each tcgen05.mma at only one every few cycles:
-    // four issue streams keep the tail after the last slice short) and accumulates into its own two TMEM
-    // accumulators; each issuer commits to mma_bar (NISSUE arrivals).
+    // One elected lane of each of the NISSUE issuer warps takes the k-steps kk = iss, iss + NISSUE, ... (each waits
+    // on its own slices' mbarriers: four wait/issue streams keep the tail after the last slice short) and
+    // accumulates into its own two TMEM accumulators; each issuer commits to mma_bar (NISSUE arrivals).
     if (elect_one()) {
       const int iss = warp_u - 8;
       const bool dbg = dbg_cta && iss == 0;
