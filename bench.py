@@ -77,28 +77,72 @@ def workload_text(B):
             % (B, AUDIO_LEN, N_WORDS))
 
 
+def reference_step_clips_per_s(sample_b, steps, warmup, threads, device="cpu"):
+    """The UNMODIFIED reference `Processor.forward_pass_s2ag` (oracle/ref_loader.py: the checkout, else the copy staged
+    in git-ignored oracle/_ref by oracle/build_ref.py), train=True, epoch 1, dropout as shipped, fp32, TF32 off.
+    device='cpu': the reference's own CPU path on `threads` host threads; device='cuda': context arm, stock
+    PyTorch/cuDNN/cuBLAS on the same B200 ('the bar for each kernel')."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    cfg, O = cfg_namespace()
+    torch.set_num_threads(threads)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1234)
+    pr = ref_loader.make_processor(O.CFG, N_WORDS, N_SPEAKERS, device=device)
+    for n in (pr.s2ag_generator, pr.s2ag_discriminator):
+        n.train()
+    batch, _, _ = O.synthetic_batch(sample_b, N_WORDS, N_SPEAKERS, AUDIO_LEN, 1234)
+    batch = tuple(t.to(device) for t in batch)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
+    for _ in range(warmup):
+        pr.forward_pass_s2ag(batch[0], batch[1], batch[2], batch[3], batch[4], train=True)
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pr.forward_pass_s2ag(batch[0], batch[1], batch[2], batch[3], batch[4], train=True)
+    sync()
+    dt = (time.perf_counter() - t0) / steps
+    return sample_b / dt, dt, ref_loader.root_used()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_b = args.cpu_sample_batch
-    steps = max(1, min(args.steps, 3))
-    warm = 1
-    v, dt = cpu_reference_clips_per_s(sample_b, steps, warm, threads)
+    gpu = args.impl == "reference-gpu"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    have_ref = ref_loader.reference_root() is not None
+    if gpu and not have_ref:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref is not staged (oracle/build_ref.py)"}))
+        return
+    if have_ref:
+        sample_b = args.ref_batch if not gpu else args.batch_per_gpu
+        steps, warm = (max(1, min(args.steps, 3)), 1) if not gpu else (max(1, min(args.steps, 10)), 2)
+        v, dt, root = reference_step_clips_per_s(sample_b, steps, warm, threads, "cuda" if gpu else "cpu")
+        kind = "reference"
+        what = ("UNMODIFIED reference Processor.forward_pass_s2ag (%s), %s, train=True, dropout as shipped, fp32"
+                % ("oracle/_ref staged copy" if root.endswith("_ref") else "reference checkout",
+                   "stock PyTorch/cuDNN on cuda:0, TF32 off" if gpu else "%d host threads" % threads))
+    else:
+        sample_b, steps, warm = args.cpu_sample_batch, max(1, min(args.steps, 3)), 1
+        v, dt = cpu_reference_clips_per_s(sample_b, steps, warm, threads)
+        kind = "port"
+        what = "oracle port of processor_v2.forward_pass_s2ag (reference not staged), dropout off"
     line = {
-        "impl": "reference", "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step",
+        "impl": args.impl, "metric": "gesture-clips/sec (34-frame, 27-D pose), full GAN training step",
         "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(args.batch_per_gpu),
-                   "sample": "bounded sample of that workload: %d clips per timed iteration, dropout off" % sample_b},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
-                         "sample": "%d timed GAN iterations of %d clips (oracle port of processor_v2.forward_pass_s2ag, "
-                                   "dropout off)" % (steps, sample_b)},
+                   "sample": "bounded sample of that workload: %d clips per timed iteration" % sample_b},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads if not gpu else 0, "kind": kind,
+                         "sample": "%d timed GAN iterations of %d clips after %d warm-up; %s" % (steps, sample_b, warm, what)},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
 
 
 # ncu --set full capture of the roofline launch (profiles/r01_ncu_umma_gemm.txt): dram__bytes_read.sum + dram__bytes_write.sum
@@ -191,7 +235,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--ref-batch", type=int, default=128,
+                    help="clips per timed iteration of the reference CPU arm (BASELINE config 2 batch)")
     ap.add_argument("--batch-per-gpu", type=int, default=256)
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true")
@@ -201,7 +247,7 @@ def main():
     ap.add_argument("--roofline-only", action="store_true", help="run only the roofline kernel (for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.impl != "ours":
         return run_reference_arm(args)
 
     import torch
@@ -326,10 +372,21 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = cpu_reference_clips_per_s(args.cpu_sample_batch, 1, 1, threads)
-        cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
-               "sample": "1 timed GAN iteration of %d clips after 1 warm-up (oracle port of "
-                         "processor_v2.forward_pass_s2ag, dropout off, %d torch threads)" % (args.cpu_sample_batch, threads)}
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_loader
+        if ref_loader.reference_root() is not None:
+            v, dt, root = reference_step_clips_per_s(args.ref_batch, 2, 1, threads, "cpu")
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "reference",
+                   "sample": "2 timed GAN iterations of %d clips after 1 warm-up (UNMODIFIED reference "
+                             "Processor.forward_pass_s2ag from %s, dropout as shipped, %d torch threads)"
+                             % (args.ref_batch, "oracle/_ref" if root.endswith("_ref") else "the reference checkout",
+                                threads)}
+        else:
+            v, dt = cpu_reference_clips_per_s(args.cpu_sample_batch, 1, 1, threads)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                   "sample": "1 timed GAN iteration of %d clips after 1 warm-up (oracle port of "
+                             "processor_v2.forward_pass_s2ag, dropout off, %d torch threads)"
+                             % (args.cpu_sample_batch, threads)}
 
     if rank == 0:
         line = {

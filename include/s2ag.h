@@ -240,6 +240,45 @@ int s2ag_adam_step(float* p, const float* g, float* m, float* v, long n, float l
 int s2ag_attention_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                        float* out, float* alpha, int N, int T, int Hd, int A, void* stream);
 
+/* backward of s2ag_attention_fwd.  d_out[N,Hd], d_alpha[N,T] (may be NULL) -> dx[N,T,Hd];
+ * dw1[A,Hd] +=, db1[A] +=, dw2[A] +=, db2[1] +=.  A <= 64. */
+int s2ag_attention_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* alpha,
+                       const float* d_out, const float* d_alpha, float* dx, float* dw1, float* db1,
+                       float* dw2, float* db2, int N, int T, int Hd, int A, void* stream);
+
+/* ---- input front-end ---------------------------------------------------
+ * utils/common.py:340-349 get_mfcc_features == librosa.feature.mfcc(y, sr, n_mfcc)/1000 (STFT n_fft 2048, hann,
+ * centre + reflect padding, |.|^2, slaney mel bank, power_to_db(top_db), DCT-II ortho) and its 1st / 2nd row differences;
+ * called per chunk at processor_v2.py:1249-1252.  audio[B, lda >= L]; mel_fb[n_mels, 1025] with mel_span[n_mels][2] =
+ * [lo, hi) non-zero bin range of each filter; dct[n_mfcc, n_mels]; logmel_ws[B, F, n_mels] workspace, F = 1 + L/hop;
+ * out[B, 3*n_mfcc - 5, F] (the layout PoseGenerator.forward takes); scale = 1/1000. */
+int s2ag_mfcc_features(const float* audio, long lda, int B, int L, int hop, const float* mel_fb,
+                       const int* mel_span, int n_mels, const float* dct, int n_mfcc, float top_db,
+                       float scale, float* logmel_ws, float* out, void* stream);
+/* processor_v2.py:606-610 on the device: audio_out[B,L] = int16 audio * audio_max[B] / 32767 (audio_max fp32, or fp64
+ * when max_is_f64: same roundings as numpy), mfcc_out[n] = fp16 -> fp32.  Either half may be skipped with NULL. */
+int s2ag_expand_inputs(const void* audio_i16, const void* audio_max, int max_is_f64, float* audio_out,
+                       long B, long L, const void* mfcc_f16, float* mfcc_out, long n_mfcc, void* stream);
+
+/* ---- long-form synthesis on the device (processor_v2.py:1282-1327, 1334-1391) -----------
+ * chunk `chunk` of every clip: out[B,T,P] -> result[b, chunk*(T-n_pre) + t, :] with the first n_pre frames blended
+ * linearly with what the previous chunk left there (prev*(n-j)/(n+1) + next*(j+1)/(n+1)); pre_next[B,T,P+1] (may be
+ * NULL) = seed of the next chunk: zeros, first n_pre frames = RAW last n_pre frames of out, constraint bit 1.
+ * n_chunks[B] (may be NULL): clips with chunk >= n_chunks[b] are left untouched (ragged clip lengths). */
+int s2ag_longform_blend(const float* out, float* result, long ld_result, float* pre_next,
+                        const int* n_chunks, int chunk, int B, int T, int P, int n_pre, void* stream);
+/* fade to the mean pose: seq[b] (ld_seq floats per clip, Lmax frames capacity, len[b] valid frames) is zero-padded to
+ * end = start_frame[b] + 2*n_smooth, frames [end - n_smooth, len) zeroed, then [start, end) replaced by its weighted
+ * (5,1,...,1,5) quadratic least-squares fit; len_out[b] = max(len[b], end). */
+int s2ag_fade_out(float* seq, long ld_seq, const int* len, const int* start_frame, int* len_out, int B, int P,
+                  int n_smooth, int Lmax, void* stream);
+/* utils/ted_db_utils.py:81-102: vec[N,27] (+ mean[27] when not NULL) -> pose[N,10,3] */
+int s2ag_dir_vec_to_pose(const float* vec, const float* mean, float* pose, long N, void* stream);
+/* processor_v2.py:738-774 push_samples: dst[0] = L1(out,tgt), dst[1] = joint MAE over frames >= n_pre,
+ * dst[2] = mean |accel(tgt) - accel(out)|; out,tgt [B,T,27]; acc_ws: 3 doubles */
+int s2ag_pose_metrics(const float* out, const float* tgt, const float* mean, double* acc_ws, float* dst,
+                      int B, int T, int n_pre, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

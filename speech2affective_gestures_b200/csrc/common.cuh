@@ -46,6 +46,13 @@ void s2ag_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+// device-side assertion (mirrors the device assert nn.Embedding raises on an out-of-range index)
+#ifdef S2AG_EMU
+#define S2AG_DEVICE_TRAP() abort()
+#else
+#define S2AG_DEVICE_TRAP() __trap()
+#endif
+
 static inline int s2ag_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // activation codes shared by every epilogue (mirrors the reference's nn.LeakyReLU slopes,

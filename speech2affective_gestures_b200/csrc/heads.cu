@@ -244,6 +244,67 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restr
   }
 }
 
+// backward of the above: one block per sequence; dynamic smem: alpha/de [2T] + dw1 [A*Hd] + db1 [A] + dw2 [A]
+// d_out[N,Hd], d_alpha[N,T] (may be NULL); dx[N,T,Hd]; dw1[A,Hd] +=, db1[A] +=, dw2[A] +=, db2[1] +=
+constexpr int ATT_MAX_A = 64;
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ alpha, const float* __restrict__ d_out,
+                                                            const float* __restrict__ d_alpha, float* __restrict__ dx,
+                                                            float* __restrict__ dw1, float* __restrict__ db1,
+                                                            float* __restrict__ dw2, float* __restrict__ db2,
+                                                            int T, int Hd, int A) {
+  S2AG_DYN_SMEM(float, sm);
+  float* al = sm;            // [T]
+  float* de = sm + T;        // [T]
+  float* sw1 = de + T;       // [A*Hd]
+  float* sb1 = sw1 + A * Hd; // [A]
+  float* sw2 = sb1 + A;      // [A]
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float* xs = x + (long)n * T * Hd;
+  const float* go = d_out + (long)n * Hd;
+  for (int i = threadIdx.x; i < A * Hd + 2 * A; i += 256) sw1[i] = 0.f;
+  float part = 0.f;
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const float a = alpha[(long)n * T + t];
+    float da = d_alpha ? d_alpha[(long)n * T + t] : 0.f;
+    for (int h = 0; h < Hd; ++h) da = fmaf(go[h], xs[(long)t * Hd + h], da);
+    al[t] = a; de[t] = da;
+    part = fmaf(a, da, part);
+  }
+  const float S = block_sum(part, red);   // (also orders the smem initialisation before the atomics below)
+  float dsum = 0.f;
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const float* xr = xs + (long)t * Hd;
+    const float a = al[t];
+    const float det = a * (de[t] - S);    // softmax backward
+    dsum += det;
+    float dpre[ATT_MAX_A];
+    for (int q = 0; q < A; ++q) {
+      float d = b1[q];
+      for (int h = 0; h < Hd; ++h) d = fmaf(xr[h], __ldg(w1 + q * Hd + h), d);
+      const float v = s2ag_sigmoid(d);
+      atomicAdd(sw2 + q, det * v);
+      dpre[q] = det * w2[q] * v * (1.f - v);
+      atomicAdd(sb1 + q, dpre[q]);
+    }
+    for (int h = 0; h < Hd; ++h) {
+      float g = a * go[h];
+      for (int q = 0; q < A; ++q) {
+        g = fmaf(dpre[q], __ldg(w1 + q * Hd + h), g);
+        atomicAdd(sw1 + q * Hd + h, dpre[q] * xr[h]);
+      }
+      dx[((long)n * T + t) * Hd + h] = g;
+    }
+  }
+  const float tot = block_sum(dsum, red);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(db2, tot);
+  for (int i = threadIdx.x; i < A * Hd; i += 256) atomicAdd(dw1 + i, sw1[i]);
+  for (int i = threadIdx.x; i < A; i += 256) { atomicAdd(db1 + i, sb1[i]); atomicAdd(dw2 + i, sw2[i]); }
+}
+
 static inline int ew_blocks(long total) {
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -346,6 +407,19 @@ extern "C" int s2ag_attention_fwd(const float* x, const float* w1, const float* 
   if (N == 0) return S2AG_OK;
   auto kfn = &attention_fwd_kernel;
   S2AG_LAUNCH(kfn, N, 256, T * sizeof(float), stream, x, w1, b1, w2, b2, out, alpha, T, Hd, A);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_attention_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* alpha,
+                                  const float* d_out, const float* d_alpha, float* dx, float* dw1, float* db1,
+                                  float* dw2, float* db2, int N, int T, int Hd, int A, void* stream) {
+  S2AG_CHECK_ARG(x && w1 && b1 && w2 && alpha && d_out && dx && dw1 && db1 && dw2 && db2);
+  S2AG_CHECK_ARG(N >= 0 && T > 0 && Hd > 0 && A > 0 && A <= ATT_MAX_A && (2 * T + A * Hd + 2 * A) * 4 <= 48 * 1024);
+  if (N == 0) return S2AG_OK;
+  auto kfn = &attention_bwd_kernel;
+  S2AG_LAUNCH(kfn, N, 256, (2 * T + A * Hd + 2 * A) * sizeof(float), stream, x, w1, b1, w2, alpha, d_out, d_alpha, dx,
+              dw1, db1, dw2, db2, T, Hd, A);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }

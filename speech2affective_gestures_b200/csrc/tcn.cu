@@ -98,24 +98,28 @@ __global__ void tcn_bwd_head_kernel(const float* __restrict__ dout, const float*
 
 // ---------------------------------------------------------------- embedding
 __global__ void embedding_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ table,
-                                     float* __restrict__ out, long ldo, long n, int D, float p,
+                                     float* __restrict__ out, long ldo, long n, int D, long V, float p,
                                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev) seed += seed_dev[0];
   const long total = n * D;
   for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long i = e / D; const int d = (int)(e % D);
-    out[i * ldo + d] = __ldg(table + idx[i] * (long)D + d) * s2ag_dropout_scale(seed, (unsigned long long)e, p);
+    const long r = idx[i];
+    if (r < 0 || r >= V) S2AG_DEVICE_TRAP();  // nn.Embedding device-asserts here too
+    out[i * ldo + d] = __ldg(table + r * (long)D + d) * s2ag_dropout_scale(seed, (unsigned long long)e, p);
   }
 }
 __global__ void embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dout, long ldo,
-                                     float* __restrict__ dtable, long n, int D, float p, unsigned long long seed,
+                                     float* __restrict__ dtable, long n, int D, long V, float p, unsigned long long seed,
                                      const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev) seed += seed_dev[0];
   const long total = n * D;
   for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long i = e / D; const int d = (int)(e % D);
     const float gsc = s2ag_dropout_scale(seed, (unsigned long long)e, p);
-    if (gsc != 0.f) atomicAdd(dtable + idx[i] * (long)D + d, dout[i * ldo + d] * gsc);
+    const long r = idx[i];
+    if (r < 0 || r >= V) S2AG_DEVICE_TRAP();
+    if (gsc != 0.f) atomicAdd(dtable + r * (long)D + d, dout[i * ldo + d] * gsc);
   }
 }
 
@@ -213,7 +217,7 @@ extern "C" int s2ag_embedding_fwd(const int64_t* idx, const float* table, float*
   if (total == 0) return S2AG_OK;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   auto kfn = &embedding_fwd_kernel;
-  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, idx, table, out, ldo, n, D, p_drop, (unsigned long long)seed,
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, idx, table, out, ldo, n, D, V, p_drop, (unsigned long long)seed,
               (const unsigned long long*)seed_dev);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
@@ -225,7 +229,7 @@ extern "C" int s2ag_embedding_bwd(const int64_t* idx, const float* dout, long ld
   if (total == 0) return S2AG_OK;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   auto kfn = &embedding_bwd_kernel;
-  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, idx, dout, ldo, dtable, n, D, p_drop, (unsigned long long)seed,
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, idx, dout, ldo, dtable, n, D, V, p_drop, (unsigned long long)seed,
               (const unsigned long long*)seed_dev);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;

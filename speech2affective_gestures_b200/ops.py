@@ -29,6 +29,10 @@ def manual_seed(seed):
     _seed_counter = itertools.count(1)
 
 
+def seed_state():
+    return _base_seed
+
+
 def next_seed():
     return (_base_seed << 20) + next(_seed_counter) * 0x9E3779B1
 
@@ -66,6 +70,10 @@ def _handle(stream, device):
         _C.call("s2ag_register_scratch", ctypes.c_void_p(h), ctypes.c_void_p(buf.data_ptr()), SCRATCH_BYTES)
         _SCRATCH[key] = buf
     return ctypes.c_void_p(h)
+
+
+def has_scratch(stream, device):
+    return (device.index, stream.cuda_stream) in _SCRATCH
 
 
 def _stream(t):
@@ -152,6 +160,7 @@ class LinearFn(torch.autograd.Function):
         ctx.t = (xr, w, y.detach())  # detached alias: storing `y` itself would tie ctx <-> output in a cycle
         ctx.cfg = (act, float(slope), M, N, K, ldx, b)
         ctx.xshape = x.shape
+        ctx.want_w = w.requires_grad  # decided at forward time (a caller may freeze the weights around one pass)
         return y
 
     @staticmethod
@@ -169,7 +178,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _empty(ctx.xshape, dy)
             _C.call("s2ag_linear_bwd_data", _p(dyr), lddy, _p(w), _p(dx), K, M, N, K, 0, st)
-        if w.requires_grad:
+        if ctx.want_w:
             db = _grad_of(b) if (b is not None and b.requires_grad) else None
             _C.call("s2ag_linear_bwd_weight", _p(dyr), lddy, _p(xr), ldx, _p(_grad_of(w)), _p(db), M, N, K, st)
         return dx, None, None, None, None, None
@@ -195,6 +204,7 @@ class LinearTFn(torch.autograd.Function):
         _C.call("s2ag_linear_t_fwd", _p(x), _p(w), _p(b), _p(yr), ldy, B, L, C, N, act, float(slope), _stream(x))
         ctx.t = (x, w, b, y.detach())
         ctx.cfg = (B, L, C, N, act, float(slope))
+        ctx.want_w = w.requires_grad
         return y
 
     @staticmethod
@@ -212,7 +222,7 @@ class LinearTFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _empty((B, L, C), dy)
             _C.call("s2ag_linear_t_bwd_data", _p(dyr), lddy, _p(w), _p(dx), B, L, C, N, st)
-        if w.requires_grad:
+        if ctx.want_w:
             db = _grad_of(b) if (b is not None and b.requires_grad) else None
             _C.call("s2ag_linear_t_bwd_weight", _p(dyr), lddy, _p(x), _p(_grad_of(w)), _p(db), B, L, C, N, st)
         return dx, None, None, None, None, None
@@ -225,7 +235,8 @@ def linear_t(x, w, b=None, act=ACT_NONE, slope=0.0, out=None):
 # ------------------------------------------------------------------------------------------ BatchNorm helper
 class _BnState:
     """The per-call record a BN forward leaves for its backward."""
-    __slots__ = ("x", "ldx", "M", "C", "mean", "invstd", "training", "act", "slope", "y", "ldy", "cmap", "pmap")
+    __slots__ = ("x", "ldx", "M", "C", "mean", "invstd", "training", "act", "slope", "y", "ldy", "cmap", "pmap",
+                 "want_w")
 
 
 _bn_repeat = [1]
@@ -272,13 +283,14 @@ def _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2=None, lda
     s = _BnState()
     s.x, s.ldx, s.M, s.C, s.mean, s.invstd, s.training = x2, ldx, M, C, mean, invstd, training
     s.act, s.slope, s.y, s.ldy, s.cmap, s.pmap = act, float(slope), y2, ldy, cmap, pmap
+    s.want_w = bn.weight.requires_grad
     return s
 
 
 def _bn_backward(s, bn, dy2, lddy, need_dx=True, dadd2=None, lddadd=0):
     ws = torch.empty(2 * s.C, dtype=torch.float64, device=dy2.device)
     dx = _empty((s.M, s.C), dy2) if need_dx else None
-    wg = bn.weight.requires_grad
+    wg = s.want_w
     _C.call("s2ag_bn_bwd", _p(dy2), lddy, _p(s.y), s.ldy, _p(s.cmap), _p(s.x), s.ldx, s.M, s.C, _p(bn.weight),
             _p(s.pmap), _p(s.mean), _p(s.invstd), 1 if s.training else 0, s.act, s.slope, _p(dx), s.C,
             _p(_grad_of(bn.weight)) if wg else None, _p(_grad_of(bn.bias)) if wg else None, _p(dadd2), lddadd,
@@ -366,6 +378,7 @@ class ConvBnActFn(torch.autograd.Function):
         ctx.geom = (N, H, W, Cin, Cout, KH, KW, sh, sw, ph, pw, dh, dw, M, act, float(slope), ldx, ldy)
         ctx.x2, ctx.w, ctx.b, ctx.y2 = x2, w, b, y2
         ctx.xshape = x.shape
+        ctx.want_w = w.requires_grad
         return y
 
     @staticmethod
@@ -383,7 +396,7 @@ class ConvBnActFn(torch.autograd.Function):
         else:
             dc, lddc = dy2, lddy
         w, b = ctx.w, ctx.b
-        if w.requires_grad:
+        if ctx.want_w:
             db = _grad_of(b) if (b is not None and b.requires_grad) else None
             side = _side_stream[0]
             cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
@@ -462,12 +475,13 @@ class EmbeddingFn(torch.autograd.Function):
                 ctypes.c_uint64(seed), _p(nonce), _stream(table))
         ctx.idx, ctx.table = idx, table
         ctx.cfg = (float(p), seed, V, D, nonce)
+        ctx.want_w = table.requires_grad
         return out
 
     @staticmethod
     def backward(ctx, dout):
         p, seed, V, D, nonce = ctx.cfg
-        if ctx.table.requires_grad:
+        if ctx.want_w:
             d2, ld = _rows(dout, D)
             _C.call("s2ag_embedding_bwd", _p(ctx.idx), _p(d2), ld, _p(_grad_of(ctx.table)), ctx.idx.numel(), D, V, p,
                     ctypes.c_uint64(seed), _p(nonce), _stream(dout))
@@ -528,6 +542,7 @@ class TcnBlockFn(torch.autograd.Function):
                 float(p), ctypes.c_uint64(seed), _p(nonce), st)
         ctx.t = (x, y1, y2, out.detach(), w1, w2, n1, n2, v1, g1, b1, v2, g2, b2)
         ctx.cfg = (B, T, C, k, dilation, float(p))
+        ctx.want_w = v1.requires_grad
         return out
 
     @staticmethod
@@ -539,7 +554,7 @@ class TcnBlockFn(torch.autograd.Function):
         dx = _empty(x.shape, x)
         dw = torch.zeros((2, C, k, C), dtype=torch.float32, device=x.device)
         ws = _empty((2, B * T * C), x)
-        train_w = v1.requires_grad
+        train_w = ctx.want_w
         db1 = _grad_of(b1) if train_w else torch.zeros_like(b1)
         db2 = _grad_of(b2) if train_w else torch.zeros_like(b2)
         _C.call("s2ag_tcn_block_bwd", _p(dout), _p(x), _p(y1), _p(y2), _p(out), _p(w1), _p(w2), _p(dx), _p(dw[0]),
@@ -602,6 +617,7 @@ class BiGruFn(torch.autograd.Function):
         if need_bwd:
             ctx.layers, ctx.params = layers, params
             ctx.cfg = (B, T, In0, H, nlayers, sum_halves, slices, len(pieces))
+            ctx.want_w = params[0].requires_grad
         return y
 
     @staticmethod
@@ -625,7 +641,7 @@ class BiGruFn(torch.autograd.Function):
             wif, whf, bif, bhf, wir, whr, bir, bhr = ctx.params[8 * l:8 * l + 8]
             need_dx = l > 0 or npieces > 0 or ctx.needs_input_grad[0]
             dxl = _empty((B, T, rec["In"]), dy) if need_dx else None
-            want_w = wif.requires_grad
+            want_w = ctx.want_w
             gw = [_p(_grad_of(q)) for q in (wif, wir, bif, bir, whf, whr, bhf, bhr)] if want_w else [None] * 8
             args = [_p(d), ldd, dstride, _p(rec["x"]), rec["ldx"], _p(rec["out"]), _p(rec["gates"]),
                     _p(wif), _p(wir), _p(whf), _p(whr), _p(dxl), rec["In"], *gw]
@@ -721,6 +737,7 @@ class DHeadFn(torch.autograd.Function):
         out = _empty((B, 1), g)
         _C.call("s2ag_dhead_fwd", _p(g), _p(w1), _p(b1), _p(w2), _p(b2), _p(lin1), _p(out), B, T, H, _stream(g))
         ctx.t = (g, lin1, out.detach(), w1, b1, w2, b2)
+        ctx.want_w = w1.requires_grad
         return out
 
     @staticmethod
@@ -729,7 +746,7 @@ class DHeadFn(torch.autograd.Function):
         B, T, H2 = g.shape
         dout = dout.contiguous()
         dg = _empty(g.shape, g) if ctx.needs_input_grad[0] else None
-        if w1.requires_grad:
+        if ctx.want_w:
             gw1, gb1, gw2, gb2 = _grad_of(w1), _grad_of(b1), _grad_of(w2), _grad_of(b2)
         else:
             gw1, gb1, gw2, gb2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2)
@@ -782,15 +799,132 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count, grad_scale=1.0):
             float(grad_scale), _p(step_count), _stream(p))
 
 
+class AttentionFn(torch.autograd.Function):
+    """sigmoid-MLP score + softmax over time + weighted sum (net/ser_att_conv_rnn_v2.py:30-34), forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        _check(x, w1, b1, w2, b2)
+        x = x.contiguous()
+        N, T, Hd = x.shape
+        A = w1.shape[0]
+        out = _empty((N, Hd), x)
+        alpha = _empty((N, T, 1), x)
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        _C.call("s2ag_attention_fwd", _p(x), _p(w1c), _p(b1), _p(w2c), _p(b2), _p(out), _p(alpha), N, T, Hd, A,
+                _stream(x))
+        ctx.t = (x, w1, b1, w2, b2, w1c, w2c, alpha.detach())
+        ctx.want_w = w1.requires_grad
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, d_out, d_alpha):
+        x, w1, b1, w2, b2, w1c, w2c, alpha = ctx.t
+        N, T, Hd = x.shape
+        A = w1.shape[0]
+        dx = _empty(x.shape, x)
+        if ctx.want_w:
+            gw1, gb1, gw2, gb2 = _grad_of(w1), _grad_of(b1), _grad_of(w2), _grad_of(b2)
+        else:
+            gw1, gb1, gw2, gb2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2)
+        if d_out is None:
+            d_out = torch.zeros(N, Hd, dtype=torch.float32, device=x.device)
+        _C.call("s2ag_attention_bwd", _p(x), _p(w1c), _p(b1), _p(w2c), _p(alpha), _p(d_out.contiguous()),
+                _p(None if d_alpha is None else d_alpha.contiguous()), _p(dx), _p(gw1), _p(gb1), _p(gw2), _p(gb2),
+                N, T, Hd, A, _stream(x))
+        return dx, None, None, None, None
+
+
 def attention(x, w1, b1, w2, b2):
-    """sigmoid-MLP score + softmax over time + weighted sum (net/ser_att_conv_rnn_v2.py:30-34).
-    -> (out[N,Hd], alphas[N,T,1])"""
-    _check(x, w1, b1, w2, b2)
-    x = x.contiguous()
-    N, T, Hd = x.shape
-    A = w1.shape[0]
-    out = _empty((N, Hd), x)
-    alpha = _empty((N, T, 1), x)
-    _C.call("s2ag_attention_fwd", _p(x), _p(w1.contiguous()), _p(b1), _p(w2.contiguous()), _p(b2), _p(out), _p(alpha),
-            N, T, Hd, A, _stream(x))
-    return out, alpha
+    """-> (out[N,Hd], alphas[N,T,1]); differentiable w.r.t. x and (accumulating into .grad) the four parameters."""
+    return AttentionFn.apply(x, w1, b1, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------ input front-end (SURVEY 8f)
+_MFCC_CONST = {}
+
+
+def mfcc_features(audio, sr=16000, num_mfcc=14):
+    """utils/common.py:340-349 `get_mfcc_features` for a batch of raw-audio chunks on the device:
+    audio [B, L] fp32 -> [B, 3*num_mfcc - 5, 1 + L // 512] (37 x 71 for the reference's 36 266-sample chunks)."""
+    from .utils import audio_features as af
+    _check(audio)
+    audio, lda = _rows(audio, audio.shape[-1])
+    B, L = audio.shape
+    key = (str(audio.device), sr, num_mfcc)
+    if key not in _MFCC_CONST:
+        bank, span = af.mel_bank(sr)
+        _MFCC_CONST[key] = (torch.from_numpy(bank).to(audio.device), torch.from_numpy(span).to(audio.device),
+                            torch.from_numpy(af.dct_rows(num_mfcc)).to(audio.device))
+    bank, span, dct = _MFCC_CONST[key]
+    F = 1 + L // af.HOP
+    ws = _empty((B, F, af.N_MELS), audio)
+    out = _empty((B, 3 * num_mfcc - 5, F), audio)
+    _C.call("s2ag_mfcc_features", _p(audio), lda, B, L, af.HOP, _p(bank), _p(span), af.N_MELS, _p(dct), num_mfcc,
+            float(af.TOP_DB), 1.0 / 1000.0, _p(ws), _p(out), _stream(audio))
+    return out
+
+
+def expand_inputs(audio_i16=None, audio_max=None, mfcc_f16=None, audio_out=None, mfcc_out=None):
+    """processor_v2.py:606-610 on the device: int16 audio * audio_max / 32767 -> fp32, fp16 MFCC -> fp32.
+    The compressed tensors are what crosses PCIe.  -> (audio fp32 or None, mfcc fp32 or None)"""
+    ref = audio_i16 if audio_i16 is not None else mfcc_f16
+    B = L = 0
+    is64 = 0
+    if audio_i16 is not None:
+        assert audio_i16.dtype == torch.int16 and audio_i16.is_contiguous()
+        B, L = audio_i16.shape
+        assert audio_max.dtype in (torch.float32, torch.float64) and audio_max.numel() == B
+        is64 = 1 if audio_max.dtype == torch.float64 else 0
+        if audio_out is None:
+            audio_out = torch.empty((B, L), dtype=torch.float32, device=ref.device)
+    n = 0
+    if mfcc_f16 is not None:
+        assert mfcc_f16.dtype == torch.float16 and mfcc_f16.is_contiguous()
+        n = mfcc_f16.numel()
+        if mfcc_out is None:
+            mfcc_out = torch.empty(mfcc_f16.shape, dtype=torch.float32, device=ref.device)
+    _C.call("s2ag_expand_inputs", _p(audio_i16), _p(audio_max), is64, _p(audio_out if audio_i16 is not None else None),
+            B, L, _p(mfcc_f16), _p(mfcc_out if mfcc_f16 is not None else None), n,
+            _stream(ref) if ref.is_cuda else None)
+    return (audio_out if audio_i16 is not None else None), (mfcc_out if mfcc_f16 is not None else None)
+
+
+# ------------------------------------------------------------------------------------------ long-form pipeline / metrics
+def longform_blend(out, result, chunk, n_pre, pre_next=None, n_chunks=None):
+    """processor_v2.py:1282-1327 for a batch in lock-step (see s2ag_longform_blend)."""
+    B, T, P = out.shape
+    assert result.is_contiguous() and result.shape[0] == B and result.shape[2] == P
+    _C.call("s2ag_longform_blend", _p(out.contiguous()), _p(result), result.shape[1] * P, _p(pre_next), _p(n_chunks),
+            int(chunk), B, T, P, int(n_pre), _stream(out))
+
+
+def fade_out(seq, lengths, start_frames, n_smooth):
+    """processor_v2.py:1334-1391 on [B, Lmax, P] sequences; lengths/start_frames int32 [B].  -> new lengths int32 [B]"""
+    assert seq.is_contiguous()
+    B, Lmax, P = seq.shape
+    new_len = torch.empty_like(lengths)
+    _C.call("s2ag_fade_out", _p(seq), Lmax * P, _p(lengths), _p(start_frames), _p(new_len), B, P, int(n_smooth), Lmax,
+            _stream(seq))
+    return new_len
+
+
+def dir_vec_to_pose(vec, mean=None):
+    """utils/ted_db_utils.py:81-102 (+ mean direction vector): [..., 27] -> [..., 10, 3]"""
+    vec = vec.contiguous()
+    N = vec.numel() // 27
+    pose = _empty(tuple(vec.shape[:-1]) + (10, 3), vec)
+    _C.call("s2ag_dir_vec_to_pose", _p(vec), _p(mean), _p(pose), N, _stream(vec))
+    return pose
+
+
+def pose_metrics(out, target, mean, n_pre, dst=None):
+    """processor_v2.py:738-774: -> float32[3] device tensor (L1, joint MAE, accel difference)"""
+    out, target = out.contiguous(), target.contiguous()
+    B, T, P = out.shape
+    assert P == 27
+    if dst is None:
+        dst = _empty((3,), out)
+    ws = torch.empty(3, dtype=torch.float64, device=out.device)
+    _C.call("s2ag_pose_metrics", _p(out), _p(target), _p(mean), _p(ws), _p(dst), B, T, int(n_pre), _stream(out))
+    return dst

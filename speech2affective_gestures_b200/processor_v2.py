@@ -39,7 +39,8 @@ def get_epoch_and_loss(path_to_model_files, epoch='best'):
         return None, None, np.inf
     found = []
     for f in os.listdir(path_to_model_files):
-        m = re.match(r"epoch_(\d+)_loss_([0-9.]+)_model\.pth\.tar$", f)
+        # the saved metric is L1(ours) - L1(tri-modal): negative exactly when the model beats the baseline
+        m = re.match(r"epoch_(\d+)_loss_(-?(?:[0-9.]+(?:e[-+]?\d+)?|inf|nan))_model\.pth\.tar$", f)
         if m:
             found.append((int(m.group(1)), float(m.group(2)), f))
     if not found:
@@ -244,6 +245,8 @@ class Processor(object):
                 eps_t = None
                 if getattr(Tri, 'speaker_embedding', None) is not None:
                     eps_t = en.draw_eps(torch.empty(vid_indices.shape[0], Tri.z_size, device=self.device))
+                    ev_e = torch.cuda.Event(); ev_e.record(main_s)   # the draw runs on the main stream
+                    sb.wait_event(ev_e)
 
                 def run_tri():
                     with torch.cuda.stream(sb):
@@ -424,19 +427,68 @@ class Processor(object):
                           torch.zeros(batch_size, T, P, device=dev),
                           torch.zeros(batch_size, dtype=torch.int64, device=dev))
         self._graph_train = train
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
+        # The capture stream is OUR stream: the warm-up iterations run on it first, so the library scratch buffer of
+        # the packed-operand contractions is registered for it before the capture starts (ops._handle never allocates
+        # during a capture; a stream first seen while capturing would fall back to the unpacked contraction).
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream()
+        cs = self._capture_stream
+        snap = self._snapshot_state() if train else None   # warm-up iterations must not train the live model
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            for _ in range(max(1, warmup)):
                 self.gan_step_async(*self.static_in, train)
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(cs)
         torch.cuda.synchronize()
+        if snap is not None:
+            self._restore_state(snap)
+        for st in (cs, self._side_stream, self._side_stream_b):
+            assert st is None or ops.has_scratch(st, dev), "a stream of the captured step has no registered scratch"
         import gc
         gc.collect()  # no autograd graph of the warm-up passes may survive into the capture
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        bn_mods = [m for n in (self.s2ag_generator, self.s2ag_discriminator, self.trimodal_generator)
+                   for m in n.modules() if hasattr(m, "_s2ag_batches")]
+        before = [m._s2ag_batches for m in bn_mods]
+        with torch.cuda.graph(self._graph, stream=cs):
             self.gan_step_async(*self.static_in, train)
+        # BatchNorm's num_batches_tracked is a host-side counter on this path: remember what one iteration adds so
+        # that replay_step() advances it; the capture pass itself did not execute
+        self._bn_replay_delta = [(m, m._s2ag_batches - b) for m, b in zip(bn_mods, before) if m._s2ag_batches != b]
+        for m, b in zip(bn_mods, before):
+            m._s2ag_batches = b
         return self._graph
+
+    def _snapshot_state(self):
+        """Everything a training iteration mutates: parameters, Adam moments/step counters, BatchNorm buffers and
+        their host-side batch counters, the dropout nonce."""
+        nets = (self.s2ag_generator, self.s2ag_discriminator, self.trimodal_generator)
+        return {
+            "flat": [n.flat_params.clone() for n in nets],
+            "bufs": [[b.clone() for b in n.buffers()] for n in nets],
+            "bnc": [[getattr(m, "_s2ag_batches", 0) for m in n.modules()] for n in nets],
+            "adam": [t.clone() for t in (self.gen_m, self.gen_v, self.dis_m, self.dis_v, self.gen_step, self.dis_step)],
+            "nonce": ops.seed_nonce(self.device).clone(), "seed": ops.seed_state(),
+            "metrics": self.metrics.clone(),
+        }
+
+    def _restore_state(self, snap, host_only=False):
+        nets = (self.s2ag_generator, self.s2ag_discriminator, self.trimodal_generator)
+        for n, c in zip(nets, snap["bnc"]):
+            for m, v in zip(n.modules(), c):
+                if hasattr(m, "_s2ag_batches"):
+                    m._s2ag_batches = v
+        if host_only:
+            return
+        for n, f, bs in zip(nets, snap["flat"], snap["bufs"]):
+            n.flat_params.copy_(f)
+            n.flat_grads.zero_()
+            for b, v in zip(n.buffers(), bs):
+                b.copy_(v)
+        for t, v in zip((self.gen_m, self.gen_v, self.dis_m, self.dis_v, self.gen_step, self.dis_step), snap["adam"]):
+            t.copy_(v)
+        ops.seed_nonce(self.device).copy_(snap["nonce"])
+        self.metrics.copy_(snap["metrics"])
 
     def load_static_inputs(self, in_text, in_audio, in_mfcc, target_poses, vid_indices):
         for dst, src in zip(self.static_in, (in_text, in_audio, in_mfcc, target_poses, vid_indices)):
@@ -469,6 +521,8 @@ class Processor(object):
 
     def replay_step(self):
         self._graph.replay()
+        for m, d in self._bn_replay_delta:
+            m._s2ag_batches += d
         return self.metrics
 
     # ------------------------------------------------------------------ data / epochs

@@ -166,6 +166,8 @@ template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; 
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline void sincospif(float x, float* s, float* c) { *s = (float)sin(M_PI * (double)x); *c = (float)cos(M_PI * (double)x); }
+static inline float cospif(float x) { return (float)cos(M_PI * (double)x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
