@@ -151,3 +151,36 @@ def push_samples_metrics(out_dir_vec, target, mean_dir_vec, n_poses, n_pre):
     mae = np.mean(np.abs(diff))
     accel = np.mean(np.abs(np.diff(tgt_j, n=2, axis=1) - np.diff(out_j, n=2, axis=1)))
     return loss, mae, accel
+
+
+# ------------------------------------------------------------------------------------------------ synthetic clip source
+def synthetic_clip(seed, duration=20.0, sr=16000, pose_fps=25.0, n_vocab_words=60, start_time=3.0):
+    """A TED-shaped clip record in the LMDB layout generate_gestures_by_dataset reads (processor_v2.py:1486-1495):
+    [words, poses, None, audio, None, None, {'vid','start_frame_no','end_frame_no','start_time','end_time'}].
+    Poses: a smooth random upper-body skeleton (10 joints x 3); audio: harmonic 'speech' bursts; words 'w<i>' with
+    (start, end) times in absolute video time."""
+    rng = np.random.RandomState(seed)
+    n_pose = int(round(duration * pose_fps))
+    t = np.arange(n_pose) / pose_fps
+    base = convert_dir_vec_to_pose(np.array([0.0154009, -0.9690125, -0.0884354, -0.0022264, -0.8655276, 0.4342174,
+                                             -0.0035145, -0.8755367, -0.4121039, -0.9236511, 0.3061306, -0.0012415,
+                                             -0.5155854, 0.8129665, 0.0871897, 0.2348464, 0.1846561, 0.8091402,
+                                             0.9271948, 0.2960011, -0.013189, 0.5233978, 0.8092403, 0.0725451,
+                                             -0.2037076, 0.1924306, 0.8196916]))
+    wob = sum(rng.normal(0, 0.03, size=(1, 10, 3)) * np.sin(2 * np.pi * rng.uniform(0.1, 1.5) * t + rng.uniform(0, 6.28)
+                                                            )[:, None, None] for _ in range(4))
+    poses = (base[None] + wob).astype(np.float32).reshape(n_pose, -1)
+    n = int(round(duration * sr))
+    ta = np.arange(n) / sr
+    f0 = rng.uniform(100, 200)
+    audio = sum(np.sin(2 * np.pi * f0 * h * ta + rng.uniform(0, 6.28)) / h ** 1.3 for h in range(1, 20))
+    audio = audio * (0.2 + 0.8 * (np.sin(2 * np.pi * 1.7 * ta) > -0.3)) + rng.normal(0, 3e-3, n)
+    audio = (0.5 * audio / np.abs(audio).max()).astype(np.float32)
+    words, cur = [], start_time + 0.1
+    while cur < start_time + duration - 0.6:
+        d = rng.uniform(0.15, 0.5)
+        words.append(['w%d' % rng.randint(4, n_vocab_words), float(cur), float(cur + d)])
+        cur += d + rng.uniform(0.02, 0.6)
+    meta = {'vid': 'vid%03d' % seed, 'start_frame_no': 10, 'end_frame_no': 10 + n_pose,
+            'start_time': start_time, 'end_time': start_time + duration}
+    return [words, poses, None, audio, None, None, meta]

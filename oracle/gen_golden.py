@@ -201,5 +201,126 @@ def main():
           os.path.getsize(os.path.join(OUT, "s2ag_reference_golden.npz")), "bytes")
 
 
+def longform():
+    """Long-form fixture: the reference's UNMODIFIED Processor.render_clip (processor_v2.py:1144-1439) on a 20 s
+    synthetic clip (10 chunks), with and without fade-out.  The only injected piece is `utils.common.mfcc`
+    (librosa.feature.mfcc, absent here) = oracle/frontend_oracle.mfcc_librosa; the reference's own
+    get_mfcc_features, chunk schedule, word placement, seed hand-off, blend, fade-out and convert_dir_vec_to_pose run
+    as shipped.  Also pins push_samples (:738-774)."""
+    import copy
+    import frontend_oracle as FO
+    import utils.common as rcmn
+    from utils.vocab import Vocab as RVocab
+    from utils.average_meter import AverageMeter
+    rcmn.mfcc = FO.mfcc_librosa
+    cfg = NS(**O.CFG)
+    spk = RVocab('vid', insert_default_tokens=False)
+    [spk.index_word('v%d' % i) for i in range(N_SPK)]
+    lang = RVocab('words')
+    [lang.index_word('w%d' % i) for i in range(4, 56)]   # some clip words (w56..w59) stay unknown -> UNK
+    G = RP.PoseGenerator(cfg, 27, N_WORDS, 300, None, 71, 37, 34, z_obj=spk)
+    T = RP.PGT(cfg, 27, N_WORDS, 300, None, z_obj=spk)
+    for i, net in enumerate((G, T)):
+        derand(net)
+        O.fill_state_dict(net.state_dict(), 100 + i)
+        net.eval()
+    eps = torch.from_numpy(np.random.RandomState(77).normal(0, 1, size=(1, 16)).astype(np.float32))
+    ren.re_parametrize = lambda mu, lv: mu + eps * torch.exp(0.5 * lv)
+    pr = RP.Processor.__new__(RP.Processor)
+    pr.s2ag_config_args, pr.pose_dim, pr.device = cfg, 27, torch.device('cpu')
+    pr.trimodal_generator, pr.s2ag_generator, pr.lang_model = T, G, lang
+    pr.args = NS(train_s2ag=True, video_save_path='/tmp')
+    pr.data_loader = {'train_data_s2ag': NS(num_mfcc=14), 'test_data_s2ag': NS(num_mfcc=14)}
+    pr.best_s2ag_loss_epoch = 0
+    fix = {}
+    seen = []
+    G.register_forward_pre_hook(lambda m, inp: seen.append((inp[1][0].numpy().copy(), inp[2][0].numpy().copy())))
+    for tag, seed, dur in (('a', 1, 20.0), ('b', 2, 9.3)):
+        clip = FO.synthetic_clip(seed, duration=dur)
+        # the reference's fade-out also re-fits the TARGET over [start_frame, end_frame) (:1362-1367) and raises when the
+        # ground-truth motion is shorter than that: give the clip 1 s more motion than audio
+        clip[6]['end_time'] += 1.0
+        name = '{}_{:.2f}_{:.2f}'.format(clip[6]['vid'], clip[6]['start_time'], clip[6]['end_time'])
+        for fade in (False, True):
+            del seen[:]
+            with torch.no_grad():
+                res = pr.render_clip({'audio_sr': 16000, 'clip_duration_range': [5, 12]}, clip[6]['vid'], 0, 1,
+                                     clip[1].copy(), clip[3].copy(), 16000, copy.deepcopy(clip[0]),
+                                     [clip[6]['start_time'], clip[6]['end_time']], test_samples=[name],
+                                     speaker_vid_idx=3, check_duration=False, fade_out=fade)
+            k = '%s_fade%d' % (tag, int(fade))
+            fix[k + '_resampled'] = np.asarray(res[0], dtype=np.float32)
+            fix[k + '_poses_tri'] = np.asarray(res[1], dtype=np.float32)
+            fix[k + '_poses'] = np.asarray(res[2], dtype=np.float32)
+            print('render_clip', k, 'frames', res[2].shape)
+            fix[tag + '_text'] = np.stack([t for t, _ in seen])      # per-chunk word placement the generator saw
+            fix[tag + '_mfcc'] = np.stack([m for _, m in seen]).astype(np.float32)   # per-chunk MFCC input
+        fix[tag + '_mfcc0'] = rcmn.get_mfcc_features(clip[3][:36266], sr=16000, num_mfcc=14).astype(np.float32)
+    fix['eps'] = eps.numpy()
+    # push_samples
+    rng = np.random.RandomState(5)
+    out = torch.from_numpy(rng.normal(0, 0.3, size=(6, 34, 27)).astype(np.float32))
+    tgt = torch.from_numpy(rng.normal(0, 0.3, size=(6, 34, 27)).astype(np.float32))
+    la, jm, ac = AverageMeter('loss'), AverageMeter('mae_on_joint'), AverageMeter('accel')
+    RP.Processor.push_samples(None, tgt.clone(), out.clone(), None, None, la, jm, ac, cfg.mean_dir_vec, 34, 4)
+    fix['push_samples'] = np.array([la.avg, jm.avg, ac.avg])
+    want = FO.push_samples_metrics(out.numpy(), tgt.numpy(), cfg.mean_dir_vec, 34, 4)
+    assert np.allclose(fix['push_samples'], want, rtol=1e-6), (fix['push_samples'], want)
+    path = os.path.join(OUT, "s2ag_longform_golden.npz")
+    np.savez_compressed(path, **fix)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def checkpoints():
+    """Reference-built state_dicts: (1) key / shape / dtype schema of the four networks in the shipped configuration,
+    (2) small-width checkpoints in the reference's file schema (processor_v2.py:1066-1067 {'gen_model_dict',
+    'dis_model_dict'}, :1034 {'trimodal_gen_dict'}) with the reference's OWN random initialisation, plus the reference's
+    eval-mode outputs for them: load_state_dict(strict=True) into this repo's classes must reproduce those outputs."""
+    import json
+    cfg = NS(**O.CFG)
+    spk = Vocab('vid', insert_default_tokens=False)
+    [spk.index_word('v%d' % i) for i in range(N_SPK)]
+    nets = dict(gen=RP.PoseGenerator(cfg, 27, N_WORDS, 300, None, 71, 37, 34, z_obj=spk),
+                tri=RP.PGT(cfg, 27, N_WORDS, 300, None, z_obj=spk), dis=RP.AffDiscriminator(27), cdis=RP.CDT(27))
+    schema = {k: [[n, list(v.shape), str(v.dtype)] for n, v in net.state_dict().items()] for k, net in nets.items()}
+    with open(os.path.join(OUT, "ref_state_dict_schema.json"), "w") as f:
+        json.dump({"n_words": N_WORDS, "n_speakers": spk.n_words, "schema": schema}, f)
+    small = dict(O.CFG)
+    small.update(hidden_size=24, hidden_size_s2eg=24, wordembed_dim=24, n_layers=2)
+    scfg = NS(**small)
+    torch.manual_seed(4242)
+    G = RP.PoseGenerator(scfg, 27, 40, 24, None, 71, 37, 34, z_obj=spk)
+    T = RP.PGT(scfg, 27, 40, 24, None, z_obj=spk)
+    D = RP.AffDiscriminator(27)
+    for net in (G, T, D):   # non-trivial running statistics
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        net.eval()
+    ck = os.path.join(OUT, "ref_ckpt_tiny")
+    os.makedirs(os.path.join(ck, "outputs"), exist_ok=True)
+    os.makedirs(os.path.join(ck, "work"), exist_ok=True)
+    torch.save({'gen_model_dict': G.state_dict(), 'dis_model_dict': D.state_dict()},
+               os.path.join(ck, "work", 'epoch_{:06d}_loss_{:.4f}_model.pth.tar'.format(22, -0.0123)))
+    torch.save({'trimodal_gen_dict': T.state_dict()}, os.path.join(ck, "outputs", "trimodal_gen.pth.tar"))
+    batch, eps_list, _ = O.synthetic_batch(3, 40, N_SPK, 36267, seed=99)
+    text, audio, mfcc, target, vid = batch
+    pre = target.new_zeros(3, 34, 28)
+    pre[:, :4, :-1] = target[:, :4]
+    pre[:, :4, -1] = 1
+    ren.re_parametrize = lambda mu, lv: mu + eps_list[0] * torch.exp(0.5 * lv)
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(ck, "expected.npz"), g_out=G(pre, text, mfcc, vid)[0].numpy(),
+                            t_out=T(pre, text, audio, vid)[0].numpy(), d_out=D(target).numpy())
+    print("wrote", ck, sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(ck) for f in fs), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1:] or ["step", "longform", "checkpoints"]
+    if "step" in what:
+        main()
+    if "longform" in what:
+        longform()
+    if "checkpoints" in what:
+        checkpoints()

@@ -38,6 +38,13 @@ def _sync_bn_counters(module, *_):
             m._s2ag_batches = 0
 
 
+def _reset_bn_counters(module, incompatible_keys):
+    """a loaded state_dict carries its own num_batches_tracked: pending host-side increments are void"""
+    for m in module.modules():
+        if hasattr(m, "_s2ag_batches"):
+            m._s2ag_batches = 0
+
+
 class FlatParamNet(nn.Module):
     """Base of the four top-level networks: owns the flat parameter / gradient buffers."""
 
@@ -46,6 +53,7 @@ class FlatParamNet(nn.Module):
         self._flat = None
         self._flat_grad = None
         self.register_state_dict_pre_hook(_sync_bn_counters)
+        self.register_load_state_dict_post_hook(_reset_bn_counters)
 
     def flatten_parameters_(self):
         """(Re)pack every parameter into one contiguous fp32 buffer and alias .data/.grad onto it."""

@@ -695,6 +695,8 @@ class ReparamTileFn(torch.autograd.Function):
         dst = dst.t
         _check(mu, logvar, eps, dst)
         B, Z = mu.shape
+        if tuple(eps.shape) != (B, Z) or tuple(logvar.shape) != (B, Z):
+            raise _C.S2agError("re-parametrisation noise must be [%d, %d], got %s" % (B, Z, tuple(eps.shape)))
         mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
         z = _empty((B, Z), mu)
         T = dst.shape[1]

@@ -1,7 +1,8 @@
 """Drop-in for the hot-path entry points of the reference's processor_v2.py `Processor`:
 constructor, `forward_pass_s2ag` (one GAN iteration, :776-957), `per_train_epoch` / `per_val_epoch` /
-`train` (:959-1069), `yield_batch` (:589-638), `generate_gestures` (:1071-1142) and a lock-step
-batched version of the long-form chunked synthesis of `render_clip` (:1144-1331).
+`train` (:959-1069), `yield_batch` (:589-638), `generate_gestures` (:1071-1142), `render_clip` (:1144-1439) and
+`generate_gestures_by_dataset` (:1441-1567); the long-form entry points render clips in lock-step batches on the
+device (longform.py).
 
 Out of scope: LMDB/npz cache writers, video rendering, FGD evaluator, BVH export.
 
@@ -35,7 +36,7 @@ M_DIS, M_HUBER, M_GEN, M_KLD, M_DIV, M_TOTAL, M_L1, M_L1_TRI = range(8)
 def get_epoch_and_loss(path_to_model_files, epoch='best'):
     """Checkpoint discovery by filename, same scheme as processor_v2.py:53-83:
     epoch_{:06d}_loss_{:.4f}_model.pth.tar; 'best' = lowest loss."""
-    if not os.path.isdir(path_to_model_files):
+    if not path_to_model_files or not os.path.isdir(path_to_model_files):
         return None, None, np.inf
     found = []
     for f in os.listdir(path_to_model_files):
@@ -500,9 +501,10 @@ class Processor(object):
         device-to-device copy, ~30 us for 40 MB) at the start of the next step."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
-            self._staging = tuple(torch.empty_like(t) for t in self.static_in)
             self._staging_free = None
         cs = self._copy_stream
+        if getattr(self, "_staging", None) is None:
+            self._staging = tuple(torch.empty_like(t) for t in self.static_in)
         if self._staging_free is not None:
             cs.wait_event(self._staging_free)   # the previous swap has consumed the staging buffers
         with torch.cuda.stream(cs):
@@ -510,14 +512,46 @@ class Processor(object):
                 dst.copy_(src, non_blocking=True)
             self._staging_ready = torch.cuda.Event()
             self._staging_ready.record(cs)
+        self._staging_kind = "fp32"
 
     def swap_in_prefetched(self):
         main = torch.cuda.current_stream()
         main.wait_event(self._staging_ready)
-        for dst, src in zip(self.static_in, self._staging):
-            dst.copy_(src, non_blocking=True)
+        if getattr(self, "_staging_c", None) is not None and self._staging_kind == "compressed":
+            text, a16, amax, m16, tgt, vid = self._staging_c
+            self.static_in[0].copy_(text, non_blocking=True)
+            ops.expand_inputs(a16, amax, m16, audio_out=self.static_in[1], mfcc_out=self.static_in[2])
+            self.static_in[3].copy_(tgt, non_blocking=True)
+            self.static_in[4].copy_(vid, non_blocking=True)
+        else:
+            for dst, src in zip(self.static_in, self._staging):
+                dst.copy_(src, non_blocking=True)
         self._staging_free = torch.cuda.Event()
         self._staging_free.record(main)
+
+    def prefetch_inputs_compressed(self, in_text, audio_i16, audio_max, mfcc_f16, target_poses, vid_indices):
+        """Like prefetch_inputs, but the batch crosses PCIe in the npz cache's own precision (int16 audio + fp32/fp64
+        per-clip scale, fp16 MFCC: processor_v2.py:231, :606-610); swap_in_prefetched() expands it on the device into
+        the graph's static inputs (csrc/frontend.cu).  20.6 instead of 40.8 MB per 256-clip step."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging_free = None
+        if getattr(self, "_staging_c", None) is None:
+            dev = self.device
+            self._staging_c = (torch.empty_like(self.static_in[0]),
+                               torch.empty(self.static_in[1].shape, dtype=torch.int16, device=dev),
+                               torch.empty(self.static_in[1].shape[0], dtype=audio_max.dtype, device=dev),
+                               torch.empty(self.static_in[2].shape, dtype=torch.float16, device=dev),
+                               torch.empty_like(self.static_in[3]), torch.empty_like(self.static_in[4]))
+        cs = self._copy_stream
+        if self._staging_free is not None:
+            cs.wait_event(self._staging_free)
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._staging_c, (in_text, audio_i16, audio_max, mfcc_f16, target_poses, vid_indices)):
+                dst.copy_(src, non_blocking=True)
+            self._staging_ready = torch.cuda.Event()
+            self._staging_ready.record(cs)
+        self._staging_kind = "compressed"
 
     def replay_step(self):
         self._graph.replay()
@@ -527,13 +561,21 @@ class Processor(object):
 
     # ------------------------------------------------------------------ data / epochs
     def _gather(self, samples, keys):
-        """npz-cache rows -> device tensors (processor_v2.py:601-611): int16 audio is rescaled on the
-        host exactly like the reference."""
+        """npz-cache rows -> device tensors (processor_v2.py:601-611).  The cache holds int16 audio + its per-clip
+        scale and fp16 MFCCs; they cross PCIe in that form (2 bytes per value) and `ops.expand_inputs` applies the
+        reference's `audio * audio_max / 32767` and the fp16 -> fp32 conversion on the device, bit-identically."""
         dev = self.device
         text = torch.from_numpy(samples['extended_word_seq'][keys]).to(dev)
         vec = torch.from_numpy(samples['vec_seq'][keys]).float().to(dev)
-        audio = torch.from_numpy(samples['audio'][keys] * samples['audio_max'][keys, None] / 32767).float().to(dev)
-        mfcc = torch.from_numpy(samples['mfcc_features'][keys].astype(np.float32)).to(dev)
+        a16 = np.ascontiguousarray(samples['audio'][keys])
+        amax = np.ascontiguousarray(samples['audio_max'][keys])
+        m16 = np.ascontiguousarray(samples['mfcc_features'][keys])
+        if a16.dtype == np.int16 and m16.dtype == np.float16 and amax.dtype in (np.float32, np.float64):
+            audio, mfcc = ops.expand_inputs(torch.from_numpy(a16).to(dev), torch.from_numpy(amax).to(dev),
+                                            torch.from_numpy(m16).to(dev))
+        else:  # a cache written in another precision: same arithmetic on the host as the reference
+            audio = torch.from_numpy(a16 * amax[:, None] / 32767).float().to(dev)
+            mfcc = torch.from_numpy(m16.astype(np.float32)).to(dev)
         return text, vec, audio, mfcc, samples['vid_indices'][keys]
 
     def yield_batch(self, train):
@@ -548,6 +590,7 @@ class Processor(object):
             if spk is not None and spk.__class__.__name__ == 'Vocab':
                 pool = np.setdiff1d(list(spk.word2index.values()), cur_vids)  # speakers NOT in this batch (:625-630)
                 vids = torch.from_numpy(np.random.choice(pool, size=bs)).long().to(self.device)
+                self._check_speaker_ids(vids)
             yield text, vec, audio, mfcc, vids
 
     def per_train_epoch(self):
@@ -584,7 +627,8 @@ class Processor(object):
     def load_model_at_epoch(self, epoch='best'):
         name, e, l = get_epoch_and_loss(self.args.work_dir_s2ag, epoch=epoch)
         if name is None:
-            print('Warning! No saved model found.')
+            print('Warning! No saved model found.' if epoch == 'best' else
+                  'Warning! No saved model found at epoch {}.'.format(epoch))
             return False
         self.best_s2ag_loss_epoch, self.best_s2ag_loss = e, l
         loaded = torch.load(os.path.join(self.args.work_dir_s2ag, name), map_location=self.device)
@@ -601,17 +645,29 @@ class Processor(object):
         return False  # synthetic runs: random-init frozen baseline
 
     def train(self):
+        """processor_v2.py:1032-1069: frozen baseline from outputs/trimodal_gen.pth.tar (random-init when the file is
+        absent: synthetic runs), optional resume, epoch loop with validation and checkpointing (rank 0 writes)."""
         self.load_trimodal()
-        start = 0
-        if getattr(self.args, "s2ag_load_last_best", False) and self.load_model_at_epoch(self.args.s2ag_start_epoch):
-            start = self.best_s2ag_loss_epoch
-        for epoch in range(start, self.args.s2ag_num_epoch):
+        if getattr(self.args, "s2ag_load_last_best", False):
+            found = self.load_model_at_epoch(epoch=self.args.s2ag_start_epoch)
+            if not found and self.args.s2ag_start_epoch != 'best':
+                print('Warning! Trying to load best known model for s2ag: ', end='')
+                found = self.load_model_at_epoch(epoch='best')
+                print('loaded.' if found else 'none found.')
+            self.args.s2ag_start_epoch = self.best_s2ag_loss_epoch if found else 0
+            if not found:
+                print('Warning! Starting at epoch 0')
+        else:
+            self.args.s2ag_start_epoch = 0
+        for epoch in range(self.args.s2ag_start_epoch, self.args.s2ag_num_epoch):
             self.meta_info['epoch'] = epoch
             self.io.print_log('s2ag training epoch: {}'.format(epoch))
             self.per_train_epoch()
+            self.io.print_log('Done.')
             if epoch % self.args.val_interval == 0 or epoch + 1 == self.args.s2ag_num_epoch:
                 self.io.print_log('s2ag val epoch: {}'.format(epoch))
                 self.per_val_epoch()
+                self.io.print_log('Done.')
             if self.rank == 0 and (self.s2ag_loss_updated or
                                    (epoch % self.args.save_interval == 0 and epoch > self.min_train_epochs)):
                 os.makedirs(self.args.work_dir_s2ag, exist_ok=True)
@@ -623,8 +679,12 @@ class Processor(object):
     # ------------------------------------------------------------------ inference entry points
     def generate_gestures(self, samples_to_generate=10, randomized=True, load_saved_model=True,
                           s2ag_epoch='best', make_video=False, calculate_metrics=True):
-        """34-frame batched evaluation (processor_v2.py:1071-1142): eval mode, batch 2048, the full
-        step under no_grad.  Returns {'loss': mean L1 ours, 'loss_trimodal': ..., 'clips': n}."""
+        """34-frame batched evaluation (processor_v2.py:1071-1142): eval mode, batch 2048, the full step under
+        no_grad; L1 / joint MAE / acceleration difference of `push_samples` (:738-774) are reduced on the device
+        (csrc/longform.cu) and read back once at the end.  Returns the reference's loss_dict (plus 'accel*', 'clips').
+        FGD (EmbeddingSpaceEvaluator) needs an external checkpoint and is out of scope."""
+        if make_video:
+            raise NotImplementedError("video rendering is outside the hot path (SURVEY 8)")
         if load_saved_model:
             assert self.load_model_at_epoch(epoch=s2ag_epoch), 'Speech to emotive gestures model not found'
             self.load_trimodal()
@@ -633,59 +693,221 @@ class Processor(object):
         batch_size = 2048
         test = self.data_loader['test_data_s2ag'].samples
         n = min(samples_to_generate, self.num_test_samples)
-        acc = torch.zeros(2, device=self.device)
+        cfg = self.s2ag_config_args
+        mean = torch.tensor(np.squeeze(np.array(cfg.mean_dir_vec)), dtype=torch.float32, device=self.device)
+        acc = torch.zeros(2, 3, device=self.device)   # rows: ours, tri-modal; cols: L1, joint MAE, accel (AverageMeter sums)
         start_time = time.time()
+        spk_values = np.array(list(self.test_speaker_model.word2index.values()))
         for s in range(0, n, batch_size):
             keys = np.arange(s, min(n, s + batch_size))
             if randomized:
                 keys = np.random.choice(self.num_test_samples, size=len(keys), replace=False)
-            text, vec, audio, mfcc, vids = self._gather(test, keys)
-            vids = torch.from_numpy(vids).long().to(self.device)
+            text, vec, audio, mfcc, _ = self._gather(test, keys)
+            # return_batch draws a random speaker of the test speaker model per sample (:722-724)
+            vids = torch.from_numpy(np.random.choice(spk_values, size=len(keys))).long().to(self.device)
+            self._check_speaker_ids(vids)
             with torch.no_grad():
-                m = self.gan_step_async(text, audio, mfcc, vec, vids, train=False)
-            acc += m[M_L1:M_L1_TRI + 1] * len(keys)
-        l1, l1_tri = (acc / n).tolist()
-        print('[VAL Trimodal]\tloss: {:.3f} / [VAL Ours]\tloss: {:.3f} / {:.1f}s'.format(l1_tri, l1,
-                                                                                         time.time() - start_time))
-        return {'loss': l1, 'loss_trimodal': l1_tri, 'clips': n}
+                self.gan_step_async(text, audio, mfcc, vec, vids, train=False)
+                if calculate_metrics:
+                    acc[0] += ops.pose_metrics(self.last_out, vec, mean, cfg.n_pre_poses) * len(keys)
+                    acc[1] += ops.pose_metrics(self.last_out_trimodal, vec, mean, cfg.n_pre_poses) * len(keys)
+        (l1, mae, accel), (l1_t, mae_t, accel_t) = (acc / max(n, 1)).tolist()
+        elapsed = time.time() - start_time
+        print('[VAL Trimodal]\tloss: {:.3f}, joint mae: {:.3f} / {:.1f}s'.format(l1_t, mae_t, elapsed))
+        print('[VAL Ours]\t\tloss: {:.3f}, joint mae: {:.3f} / {:.1f}s'.format(l1, mae, elapsed))
+        print('Total time taken: {:.2f} seconds.'.format(time.time() - start_time))
+        return {'loss_trimodal': l1_t, 'joint_mae_trimodal': mae_t, 'loss': l1, 'joint_mae': mae,
+                'accel_trimodal': accel_t, 'accel': accel, 'clips': n}
+
+    def _check_speaker_ids(self, vids):
+        """nn.Embedding device-asserts on an out-of-range id (and so does csrc/tcn.cu); fail on the host with a message
+        instead: the generator's speaker table is sized from the TRAIN speaker model (:147-150)."""
+        emb = getattr(self.s2ag_generator, "speaker_embedding", None)
+        if emb is not None and vids is not None and vids.numel():
+            rows = emb[0].weight.shape[0]
+            hi = int(vids.max())
+            if hi >= rows or int(vids.min()) < 0:
+                raise IndexError("speaker id %d outside the generator's speaker table (%d rows)" % (hi, rows))
+
+    def render_clip(self, data_params, vid_name, sample_idx, samples_to_generate,
+                    clip_poses, clip_audio, sample_rate, clip_words, clip_time,
+                    test_samples=None, clip_idx=0, unit_time=None, speaker_vid_idx=0, check_duration=True,
+                    fade_out=False, make_video=False, save_pkl=False):
+        """Same signature / returns as processor_v2.py:1144-1439: chunked autoregressive synthesis of one clip
+        (unit 34 frames, stride 30, seed hand-off of 4 frames, linear blend, optional quadratic fade-out), then
+        direction vectors -> joints.  -> (clip_poses_resampled, out_poses_trimodal, out_poses).
+        One clip is a lock-step batch of 1; `generate_gestures_by_dataset` renders many clips per batch."""
+        from . import longform
+        if make_video:
+            raise NotImplementedError("video rendering is outside the hot path (SURVEY 8)")
+        if test_samples is not None and \
+                '{}_{:.2f}_{:.2f}'.format(vid_name, clip_time[0], clip_time[1]) not in test_samples:
+            return [], [], [], []
+        if check_duration:
+            dur = clip_time[1] - clip_time[0]
+            if dur < data_params['clip_duration_range'][0] or dur > data_params['clip_duration_range'][1]:
+                return None, None, None
+        pc = self._prepare_clip(vid_name, clip_poses, clip_audio, sample_rate, clip_words, clip_time, unit_time,
+                                speaker_vid_idx, clip_idx)
+        print('Sample {} of {}'.format(sample_idx + 1, samples_to_generate))
+        (res,) = longform.render_lockstep(self, [pc], fade_out=fade_out, audio_sr=data_params.get('audio_sr', sample_rate))
+        if save_pkl:
+            self._save_pkl(pc, res, fade_out, data_params.get('audio_sr', sample_rate))
+        self.last_render = dict(out_dir_vec_trimodal=res[0], out_dir_vec=res[1])
+        return pc.clip_poses_resampled, res[2], res[3]
+
+    def _prepare_clip(self, vid_name, clip_poses, clip_audio, sample_rate, clip_words, clip_time, unit_time,
+                      speaker_vid_idx, clip_idx=0):
+        from . import longform
+        return longform.prepare_clip(self.s2ag_config_args, self.lang_model, self.pose_dim, vid_name, clip_poses,
+                                     clip_audio, sample_rate, clip_words, clip_time, unit_time, speaker_vid_idx,
+                                     n_speakers=self.s2ag_generator.z_obj.n_words if self.s2ag_generator.z_obj else None,
+                                     clip_idx=clip_idx)
+
+    def _save_pkl(self, pc, res, fade_out, audio_sr):
+        """processor_v2.py:1418-1437 (two pickles per clip)"""
+        import pickle
+        mean = np.squeeze(np.array(self.s2ag_config_args.mean_dir_vec))
+        prefix = '{}_s{}_{:.2f}_{:.2f}'.format(pc.vid_name, pc.speaker_vid_idx, pc.clip_time[0], pc.clip_time[1])
+        sentence = ' '.join(w[0] for w in pc.clip_words)
+        os.makedirs(self.args.video_save_path, exist_ok=True)
+        for tag, vec, poses in (('trimodal', res[0], res[2]), ('s2ag', res[1], res[3])):
+            if vec is None:
+                continue
+            with open(os.path.join(self.args.video_save_path, '{}_{}.pkl'.format(prefix, tag)), 'wb') as f:
+                pickle.dump({'sentence': sentence, 'audio': np.asarray(pc.clip_audio, dtype=np.float32),
+                             'out_dir_vec': vec + mean, 'out_poses': poses,
+                             'aux_info': '{}_{}_{}'.format(pc.vid_name, pc.speaker_vid_idx, pc.clip_idx),
+                             'human_dir_vec': pc.target_dir_vec + mean}, f)
+
+    def generate_gestures_by_dataset(self, dataset, data_params, check_duration=True,
+                                     samples=None, randomized=True, fade_out=False,
+                                     load_saved_model=True, s2ag_epoch='best',
+                                     make_video=False, save_pkl=False):
+        """Same signature as processor_v2.py:1441-1444.  dataset 'ted_db': the clip records
+        `(words, poses, _, audio, _, _, {'vid','start_frame_no','end_frame_no','start_time','end_time'})` come from
+        `data_params['clips']` (any iterable in the LMDB record layout of :1486-1495) or, when the `lmdb` module and
+        `data_params['env_file']` are available, from that LMDB; consecutive records of one video are merged exactly
+        like :1497-1523 and every merged clip goes through the chunked synthesis of `render_clip`.  B200-first: merged
+        clips are queued and rendered `data_params['lockstep_batch']` (default 256) at a time in lock-step
+        (longform.render_lockstep) instead of one by one.  Returns the list of per-clip results
+        (vid_name, clip_poses_resampled, out_poses_trimodal, out_poses); the reference returns None."""
+        from . import longform
+        if make_video:
+            raise NotImplementedError("video rendering is outside the hot path (SURVEY 8)")
+        if load_saved_model:
+            assert self.load_model_at_epoch(epoch=s2ag_epoch), 'Speech to emotive gestures model not found'
+            self.load_trimodal()
+        for net in (self.trimodal_generator, self.s2ag_generator, self.s2ag_discriminator):
+            net.eval()
+        overall_start_time = time.time()
+        if dataset.lower() != 'ted_db':
+            raise NotImplementedError("only the 'ted_db' record layout is supported (GENEA BVH I/O is out of scope)")
+        if 'clip_duration_range' not in data_params.keys():
+            data_params['clip_duration_range'] = [5, 12]
+        records = self._clip_records(data_params)
+        if randomized:
+            records = list(records)
+            records = [records[i] for i in np.random.randint(0, len(records), size=len(records))] if records else []
+        lock = int(data_params.get('lockstep_batch', 256))
+        audio_sr = data_params.get('audio_sr', self.audio_sr)
+        queue, results = [], []
+
+        def flush():
+            if not queue:
+                return
+            rendered = longform.render_lockstep(self, queue, fade_out=fade_out, audio_sr=audio_sr)
+            for pc, res in zip(queue, rendered):
+                if save_pkl:
+                    self._save_pkl(pc, res, fade_out, audio_sr)
+                results.append((pc.vid_name, pc.clip_poses_resampled, res[2], res[3]))
+            queue.clear()
+
+        def submit(vid_name, poses_all, audio_all, words_all, time_all):
+            spk = np.random.randint(0, self.test_speaker_model.n_words) if randomized else 0
+            if samples is not None and '{}_{:.2f}_{:.2f}'.format(vid_name, time_all[0], time_all[1]) not in samples:
+                return
+            if check_duration:
+                dur = time_all[1] - time_all[0]
+                if dur < data_params['clip_duration_range'][0] or dur > data_params['clip_duration_range'][1]:
+                    return
+            queue.append(self._prepare_clip(vid_name, poses_all, audio_all, audio_sr, words_all, time_all, None, spk))
+            if len(queue) >= lock:
+                flush()
+
+        clip_vid_name, frames_all = '', [-2, -2]
+        poses_all = audio_all = words_all = time_all = None
+        for video in records:
+            vid_name = video[6]['vid']
+            if not (samples is None or any(vid_name in prefix for prefix in samples)):
+                continue
+            clip_poses, clip_audio, clip_words = video[1], video[3], video[0]
+            clip_frames = [video[6]['start_frame_no'], video[6]['end_frame_no']]
+            clip_time = [video[6]['start_time'], video[6]['end_time']]
+            if vid_name != clip_vid_name or clip_frames[0] - 1 > frames_all[1]:
+                if clip_vid_name != '':
+                    # (the reference passes the NEW record's vid_name with the accumulated clip here, :1503; the
+                    # accumulated clip's own name is used instead)
+                    submit(clip_vid_name, poses_all, audio_all, words_all, time_all)
+                clip_vid_name = vid_name
+                poses_all, audio_all, words_all = clip_poses, clip_audio, list(clip_words)
+                frames_all, time_all = list(clip_frames), list(clip_time)
+            else:
+                last = clip_frames[0] - frames_all[0]
+                poses_all = np.concatenate((poses_all[:last], clip_poses), axis=0)
+                audio_all = np.concatenate((audio_all[:int((clip_time[0] - time_all[0]) * 16000)], clip_audio))
+                for word in clip_words:
+                    if word not in words_all:
+                        words_all.append(word)
+                frames_all[1] = clip_frames[1]
+                time_all[1] = clip_time[1]
+        if clip_vid_name != '' and data_params.get('render_last', True):
+            submit(clip_vid_name, poses_all, audio_all, words_all, time_all)   # (the reference drops the last clip)
+        flush()
+        print('Total time taken: {:.2f} seconds.'.format(time.time() - overall_start_time))
+        return results
+
+    @staticmethod
+    def _clip_records(data_params):
+        if 'clips' in data_params:
+            return data_params['clips']
+        try:
+            import lmdb
+            import pyarrow
+        except ImportError as e:
+            raise RuntimeError("data_params['clips'] not given and the lmdb/pyarrow reader is unavailable: %s" % e)
+        env = lmdb.open(data_params['env_file'], readonly=True, lock=False)
+        with env.begin(write=False) as txn:
+            return [pyarrow.deserialize(buf) for _, buf in txn.cursor()]
 
     @torch.no_grad()
     def synthesize_long_form(self, text_chunks, mfcc_chunks, audio_chunks, vid_indices, seed_poses=None,
                              run_trimodal=False):
-        """Lock-step batched version of render_clip's chunked autoregression (processor_v2.py:1200-1331):
-        every clip of the batch advances one 34-frame chunk at a time (stride 30); the last
-        n_pre_poses frames of a chunk seed the next (:1282-1290) and the overlap is blended linearly,
-        out[j] = prev[j]*(n-j)/(n+1) + next[j]*(j+1)/(n+1) (:1303-1327) -- all on the device.
-          text_chunks [B, n_chunks, 34] int64; mfcc_chunks [B, n_chunks, 37, 71]; audio_chunks
-          [B, n_chunks, audio_len] (only read when run_trimodal); vid_indices [B].
-        Returns dir-vec sequence [B, 34 + 30*(n_chunks-1), pose_dim]."""
+        """Tensor-level lock-step chunked synthesis over PRE-COMPUTED per-chunk inputs (BASELINE config 5):
+        text_chunks [B, n_chunks, 34] int64; mfcc_chunks [B, n_chunks, 37, 71]; audio_chunks [B, n_chunks, audio_len]
+        (only read when run_trimodal); vid_indices [B].  Seed hand-off and blend as render_clip (processor_v2.py:
+        1282-1327) on the device.  Returns the generator's dir-vec sequence [B, 34 + 30*(n_chunks-1), pose_dim]
+        (and the tri-modal baseline's as `self.last_long_form_trimodal` when run_trimodal)."""
         G = self.s2ag_generator
         G.eval()
         self.trimodal_generator.eval()
         B, n_chunks = text_chunks.shape[0], text_chunks.shape[1]
         T, P, n_pre = self.time_steps, self.pose_dim, self.s2ag_config_args.n_pre_poses
-        stride = T - n_pre
-        total = T + stride * (n_chunks - 1)
-        result = torch.zeros(B, total, P, device=self.device)
-        pre_seq = torch.zeros(B, T, P + 1, device=self.device)
+        total = T + (T - n_pre) * (n_chunks - 1)
+        seed = torch.zeros(B, T, P + 1, device=self.device)
         if seed_poses is not None:
-            pre_seq[:, :n_pre, :-1] = seed_poses[:, :n_pre]
-            pre_seq[:, :n_pre, -1] = 1
-        w_next = (torch.arange(n_pre, device=self.device, dtype=torch.float32) + 1) / (n_pre + 1)
-        w_prev = 1.0 - w_next
+            seed[:, :n_pre, :-1] = seed_poses[:, :n_pre]
+            seed[:, :n_pre, -1] = 1
+        nets = ((self.trimodal_generator, True),) if run_trimodal else ()
+        nets += ((G, False),)
+        state = [dict(result=torch.zeros(B, total, P, device=self.device), pre=seed.clone(),
+                      nxt=torch.empty_like(seed)) for _ in nets]
         for c in range(n_chunks):
-            if c > 0:
-                pre_seq.zero_()
-                pre_seq[:, :n_pre, :-1] = out[:, -n_pre:]
-                pre_seq[:, :n_pre, -1] = 1
-            if run_trimodal:
-                self.trimodal_generator(pre_seq, text_chunks[:, c], audio_chunks[:, c], vid_indices)
-            out, *_ = G(pre_seq, text_chunks[:, c], mfcc_chunks[:, c], vid_indices)
-            s = c * stride
-            if c == 0:
-                result[:, :T] = out
-            else:
-                ov = result[:, s:s + n_pre]
-                result[:, s:s + n_pre] = ov * w_prev[None, :, None] + out[:, :n_pre] * w_next[None, :, None]
-                result[:, s + n_pre:s + T] = out[:, n_pre:]
-        return result
+            for (net, is_tri), st in zip(nets, state):
+                feat = audio_chunks[:, c] if is_tri else mfcc_chunks[:, c]
+                out, *_ = net(st["pre"], text_chunks[:, c], feat, vid_indices)
+                ops.longform_blend(out, st["result"], c, n_pre, pre_next=st["nxt"])
+                st["pre"], st["nxt"] = st["nxt"], st["pre"]
+        if run_trimodal:
+            self.last_long_form_trimodal = state[0]["result"]
+        return state[-1]["result"]

@@ -14,11 +14,17 @@ class Vocab:
     """Speaker / language model stand-in.  The reference recognises a speaker model by its class
     NAME being 'Vocab' (net/multimodal_context_net_v2.py:469) and reads `.n_words`/`.word2index`."""
 
+    PAD_token, SOS_token, EOS_token, UNK_token = 0, 1, 2, 3   # utils/vocab.py:9-12
+
     def __init__(self, name, n_words, word_embedding_weights=None):
         self.name = name
         self.n_words = n_words
         self.word2index = {"w%d" % i: i for i in range(n_words)}
         self.word_embedding_weights = word_embedding_weights
+
+    def get_word_index(self, word):
+        """utils/vocab.py:64-68"""
+        return self.word2index.get(word, self.UNK_token)
 
 
 class SyntheticTedData:

@@ -38,3 +38,11 @@ def dev(request):
         _EMU["lib"] = build_emu.build()
     _C._inject_for_tests(_EMU["lib"], strict=os.environ.get("S2AG_EMU_STRICT", "1") == "1")
     return torch.device("cpu")
+
+
+@pytest.fixture(autouse=True)
+def _reset_injected_noise():
+    """the parity harness injects re-parametrisation noise through a module global: never let it leak between tests"""
+    yield
+    from speech2affective_gestures_b200.net import embedding_net as men
+    men.eps_source = None
