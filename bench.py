@@ -145,45 +145,99 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-# ncu --set full capture of the roofline launch (profiles/r01_ncu_umma_gemm.txt): dram__bytes_read.sum + dram__bytes_write.sum
-ROOFLINE_TRAFFIC_BYTES = 38848512  # 25.33 MB read + 13.52 MB written (profiles/r01_ncu_gemm_umma_pk.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same shapes (profiles/,
+# 256 clips); None where no capture of that kernel is committed
+NCU_TRAFFIC = {"gru_recurrence_fwd": 66.0e6 + 55.6e6,   # profiles/r01_ncu_gru_persist.txt
+               "gemm_gru_projection": 38848512}         # profiles/r01_ncu_gemm_umma_pk.txt
 
 
-def roofline(B, dev, lib, clips_per_s_per_gpu=None):
-    """The dense-contraction engine (gemm_umma_pk_kernel / gemm_umma_kernel, tcgen05) carries ~33 % of the step's kernel
-    time; its largest single shape is the GRU layer input projection [B*34, 600] x [600, 2*900] (both directions).
-    achieved = algorithmic 2*M*N*K / CUDA-event time of that call (weight packing + contraction); the kernel issues 3
-    bf16 MMAs per algorithmic MAC in the fp32-grade bf16x3 mode, so its tensor-pipe ceiling is 1/3 of the bf16 peak it is
-    reported against."""
-    import torch
-    from speech2affective_gestures_b200 import _C, ops
-    pk = peaks()
-    M, N, K = B * 34, 1800, 600
-    x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; y = torch.empty(M, N, device=dev)
-    bias = torch.zeros(N, device=dev)
-    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
-    st = ops._stream(x)
-    call = lambda: _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(bias), ops._p(y), N, M, N, K, 0, 0.0, st)
-    for _ in range(3):
+def _time_call(torch, call, flush, reps=10, warm=3):
+    for _ in range(warm):
         call()
     torch.cuda.synchronize()
-    reps, tot = 10, 0.0
+    tot = 0.0
     for _ in range(reps):
-        flush.zero_()  # L2 flush between timed launches
+        flush.zero_()  # L2 flush between timed launches (160 MB > 126 MB L2)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(); call(); k1.record()
         torch.cuda.synchronize()
         tot += k0.elapsed_time(k1)
-    kms = tot / reps
-    ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
-    r = {"bound": "tensor", "kernel": "gemm_umma_pk_kernel<LdPlain,EpiGeneric> (tcgen05; GRU input projection %dx%dx%d; "
-                                      "weight operand packed to bf16 hi/lo images once per call (pack_operand_kernel, "
-                                      "inside the timed call) and fetched by TMA, activation operand split on the fly)"
-                                      % (M, N, K),
-         "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
-         "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": pk["source"] + " (MEASURED_PEAKS.json bf16_tflops, burst)",
-         "kernel_ms": kms, "algorithmic_flops": 2.0 * M * N * K,
-         "l2": "160 MB buffer zeroed between timed launches"}
+    return tot / reps
+
+
+def roofline(B, dev, lib, clips_per_s_per_gpu=None):
+    """Per-kernel rooflines, each kernel timed ALONE inside this process with CUDA events on its launch stream, L2
+    flushed between launches.  `roofline` = the DOMINANT kernel by time share (profiles/: gru_persist_fwd, ~20 % of
+    the step's kernel time); `roofline_kernels` = the kernels the north star names, with SURVEY 8(d)'s algorithmic
+    FLOPs / bytes per clip x the clips one launch processes.  Tensor-bound kernels are reported against the measured
+    bf16 burst peak although they run fp32-grade bf16x3 (3 MMAs per algorithmic MAC: ceiling 1/3 of that peak)."""
+    import torch
+    from speech2affective_gestures_b200 import _C, ops
+    from speech2affective_gestures_b200.net.tcn import TemporalBlock
+    from speech2affective_gestures_b200.net.multimodal_context_net_v2 import WavEncoder
+    pk = peaks()
+    T, H = 34, 300
+    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
+    st = ops._stream(flush)
+    psrc = pk["source"] + " (MEASURED_PEAKS.json)"
+    out = []
+
+    def entry(name, kernel, bound, ms, flops, nbytes, extra=None):
+        e = {"name": name, "kernel": kernel, "bound": bound, "kernel_ms": ms, "algorithmic_flops": flops,
+             "algorithmic_bytes": nbytes, "traffic": NCU_TRAFFIC.get(name), "peak_source": psrc,
+             "l2": "160 MB buffer zeroed between timed launches"}
+        if bound == "tensor":
+            ach = flops / (ms * 1e-3) / 1e12
+            e.update(achieved=ach, peak=pk["bf16_burst"], unit="TFLOP/s", frac=ach / pk["bf16_burst"])
+        else:
+            ach = nbytes / (ms * 1e-3) / 1e9
+            e.update(achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                     tensor_tflops=flops / (ms * 1e-3) / 1e12)
+        if extra:
+            e.update(extra)
+        out.append(e)
+        return e
+
+    # (1) the recurrence of one generator-sized bidirectional GRU layer: 34 dependent steps, W_hh stationary
+    M = B * T
+    ws_floats = lib.s2ag_gru_fwd_ws_floats(B, T, H)
+    gi = torch.randn(ws_floats, device=dev) * 0.5
+    whh = torch.randn(2, 3 * H, H, device=dev) * 0.05
+    bhh = torch.zeros(2, 3 * H, device=dev)
+    o = torch.empty(B, T, 2 * H, device=dev)
+    gates = torch.empty(M * 2 * 4 * H, device=dev)
+    rec = lambda: _C.call("s2ag_gru_recurrence_fwd", ops._p(gi), ops._p(whh[0]), ops._p(whh[1]), ops._p(bhh[0]),
+                          ops._p(bhh[1]), ops._p(o), ops._p(gates), B, T, H, st)
+    ms = _time_call(torch, rec, flush)
+    dom = entry("gru_recurrence_fwd", "gru_persist_fwd_kernel (tcgen05 + TMA bulk copies; one bidirectional layer, "
+                "%d clips x %d steps x H=%d, gates saved for BPTT)" % (B, T, H), "tensor", ms,
+                2.0 * M * (3 * H) * H * 2, M * 6 * H * 4 + M * 2 * H * 4 + M * 8 * H * 4,
+                {"step_period_us": ms * 1e3 / T})
+    # (2) the dense-contraction engine on its largest shape: GRU input projection [B*34, 600] x [600, 2*900]
+    N, K = 1800, 600
+    x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; y = torch.empty(M, N, device=dev)
+    bias = torch.zeros(N, device=dev)
+    ms = _time_call(torch, lambda: _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(bias), ops._p(y), N, M, N,
+                                           K, 0, 0.0, st), flush)
+    entry("gemm_gru_projection", "pack_operand_kernel + gemm_umma_pk_kernel (tcgen05; %dx%dx%d)" % (M, N, K), "tensor",
+          ms, 2.0 * M * N * K, (M * K + N * K + M * N) * 4)
+    # (3) one causal-TCN residual block forward (weight-norm + 2 dilated convs + ReLU/residual), C=300, k=2
+    C = 300
+    tb = TemporalBlock(C, C, 2, 1, 2, 2, dropout=0.0).to(dev)
+    xt = torch.randn(B, T, C, device=dev)
+    with torch.no_grad():
+        ms = _time_call(torch, lambda: tb.forward_cl(xt), flush)
+    entry("tcn_residual_block_fwd", "weight_norm_fwd x2 + gemm_umma_pk_kernel<LdConv,EpiTcn> x2 (d=2)", "tensor", ms,
+          24.48e6 * B, 81600.0 * B)
+    # (4) the frozen baseline's WavEncoder stack (4 strided Conv1d + 3 train-mode BN + LeakyReLU), raw audio in
+    we = WavEncoder().to(dev)
+    audio = torch.rand(B, AUDIO_LEN, device=dev) - 0.5
+    with torch.no_grad():
+        ms = _time_call(torch, lambda: we(audio), flush, reps=5)
+    entry("wavencoder_fwd", "WavEncoder.forward (conv1 direct + strided convs on the tcgen05 engine, BatchNorm fused "
+          "as built)", "hbm", ms, 39.38e6 * B, 149420.0 * B)
+    r = dict(dom)
+    r["roofline_kernels"] = out
     if clips_per_s_per_gpu is not None:
         r["step_frac_of_tensor_roofline"] = clips_per_s_per_gpu * FLOP_PER_CLIP / 1e12 / pk["bf16_sustained"]
     return r

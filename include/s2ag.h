@@ -180,6 +180,12 @@ int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f, const floa
                        const float* b_ih_f, const float* b_ih_r, const float* w_hh_f, const float* w_hh_r,
                        const float* b_hh_f, const float* b_hh_r, float* gi_ws, float* out, float* gates,
                        int B, int T, int In, int H, void* stream);
+/* The recurrence of one bidirectional layer alone: gi_ws as s2ag_gru_layer_fwd leaves it (the time-batched input
+ * projection [B*T][2][3H] followed by the exchange workspace; s2ag_gru_fwd_ws_floats(B,T,H) floats in total).  The
+ * latency-bound "GRU step" kernel of the north star, exposed for measurement and for callers that batch the input
+ * projection of several passes themselves.  gates may be NULL (inference). */
+int s2ag_gru_recurrence_fwd(const float* gi_ws, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
+                            const float* b_hh_r, float* out, float* gates, int B, int T, int H, void* stream);
 /* dout[B,T,*]: gradient of the layer output; direction `d` reads columns d*dir_stride .. +H of a
  * row of stride lddout (dir_stride = H normally; 0 when both halves share the gradient of their
  * sum).  dx (may be NULL) [B,T,In] row stride lddx.  All dw / db += ; pass all eight as NULL to

@@ -197,6 +197,30 @@ extern "C" int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f,
   return S2AG_OK;
 }
 
+// The recurrence alone (gi precomputed): the latency-bound "GRU step" kernel, exposed for measurement (bench.py roofline)
+// and for callers that batch the input projection themselves.
+extern "C" int s2ag_gru_recurrence_fwd(const float* gi_ws, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
+                                       const float* b_hh_r, float* out, float* gates, int B, int T, int H, void* stream) {
+  S2AG_CHECK_ARG(gi_ws && w_hh_f && w_hh_r && b_hh_f && b_hh_r && out && B > 0 && T > 0 && H > 0);
+#ifndef S2AG_EMU
+  if (g_engine == 0 && gru_persist_supported(H) && gru_persist_ws_bytes(B, H) > 0) {
+    int rc = gru_persist_fwd(gi_ws, w_hh_f, (long)(w_hh_r - w_hh_f), b_hh_f, (long)(b_hh_r - b_hh_f), out, gates,
+                             const_cast<float*>(gi_ws) + (long)B * T * 6 * H, B, T, H, umma::g_precision == 0 ? 1 : 0,
+                             stream);
+    if (rc != S2AG_OK) { s2ag_set_error("gru_persist_fwd failed (%d)", rc); return rc; }
+    S2AG_CHECK_LAUNCH();
+    return S2AG_OK;
+  }
+#endif
+  dim3 grid(s2ag_cdiv(H, RJ), s2ag_cdiv(B, RB), 2);
+  auto kfn = &gru_step_kernel;
+  for (int s = 0; s < T; ++s)
+    S2AG_LAUNCH(kfn, grid, 256, 0, stream, gi_ws, w_hh_f, (long)(w_hh_r - w_hh_f), b_hh_f, (long)(b_hh_r - b_hh_f), out,
+                gates, B, T, H, s);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
 extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride, const float* x, long ldx,
                                   const float* out, const float* gates,
                                   const float* w_ih_f, const float* w_ih_r, const float* w_hh_f, const float* w_hh_r,
