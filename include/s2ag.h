@@ -54,7 +54,9 @@ int s2ag_set_precision(int mode);
  *   64  conv_wgrad_shift_kernel skips its red.global epilogue (timing experiment; results are wrong)
  *   128 conv_wgrad_shift_kernel wherever it is structurally applicable (default: only where it was measured faster)
  *   256 no packed-weight route: both operands of every contraction are converted on the fly
- *   512 CTA-local GRU kernels for H <= 64 (umma_gru_local.cu; measured slower, off by default) */
+ *   1024 L2-exchange GRU forward (umma_gru.cu) also where the cluster kernel (umma_gru_cluster.cu) is the default
+ *   2048 cluster GRU forward for every supported hidden size (default: H <= 80; see umma_gru_cluster.cu)
+ *   4096 cluster GRU forward: wait for every h slice before the first tcgen05.mma of a step (measurement) */
 int s2ag_debug_flags(int flags);
 /* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
  * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */
@@ -124,20 +126,22 @@ int s2ag_conv_bwd_weight(const float* dy, long ldpix_dy, const float* x, long ld
  * is how AffEncoder's view/permute regrouping (:155-171) is folded in.
  *   y[m, col_map[c]] = act( (x[m,c]-mean)/sqrt(var+eps)*gamma[pm[c]] + beta[pm[c]] + add[m, col_map[c]] )
  * training != 0: batch statistics (biased var), running stats updated with `momentum`
- * (unbiased var), save_mean/save_invstd[C] written for the backward pass.
- * ws: double[2*C] scratch. */
+ * (unbiased var), save_mean/save_invstd[groups*C] written for the backward pass.
+ * groups >= 1: the M rows are `groups` consecutive, equally sized, INDEPENDENT batches that the reference pushes
+ * through the same module one call after the other (processor_v2.py:808-809: D(target), D(out)): statistics are per
+ * group, the running statistics receive the groups' momentum updates in order.  ws: double[2*C*groups] scratch. */
 int s2ag_bn_fwd(const float* x, long ldx, int M, int C, const float* gamma, const float* beta,
                 const int32_t* param_map, float* running_mean, float* running_var,
                 int training, float momentum, float eps,
                 const float* add, long ldadd, float* y, long ldy, const int32_t* col_map,
-                int act, float slope, float* save_mean, float* save_invstd, double* ws, void* stream);
+                int act, float slope, float* save_mean, float* save_invstd, double* ws, int groups, void* stream);
 /* dx = BN'(dy * act'(y)); dgamma += ; dbeta += ; dadd (may be NULL) = dy * act'(y).
- * ws: double[2*C] scratch. */
+ * ws: double[2*C*groups] scratch; groups as in s2ag_bn_fwd. */
 int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy, const int32_t* col_map,
                 const float* x, long ldx, int M, int C, const float* gamma, const int32_t* param_map,
                 const float* save_mean, const float* save_invstd, int training, int act, float slope,
                 float* dx, long lddx, float* dgamma, float* dbeta, float* dadd, long lddadd,
-                double* ws, void* stream);
+                double* ws, int groups, void* stream);
 
 /* ---- ST-GCN adjacency contraction (tgcn.py:67-69: einsum 'nkctv,kvw->nctw') -----------------
  * x[M, V, K*C] (channel index k*C + c), A[K,V,V], y[M, V, C]:  y[m,w,c] = sum_{k,v} x[m,v,k*C+c] A[k,v,w] */

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
                                                        double* __restrict__ ws, int cb, int rpb) {
   __shared__ double r1[256];
   __shared__ double r2[256];
+  // blockIdx.z = statistics group (M rows each): independent batches that share the weights (see s2ag_bn_fwd)
+  x += (long)blockIdx.z * M * ldx; ws += (long)blockIdx.z * 2 * C;
   const int tx = threadIdx.x % cb, ty = threadIdx.x / cb, rif = 256 / cb;
   const int c = blockIdx.x * cb + tx;
   const int mbeg = blockIdx.y * rpb;
@@ -60,20 +62,35 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
   if (c >= C) return;  // no barriers below
   const int pi = pmap ? pmap[c] : c;
   const int oc = cmap ? cmap[c] : c;
+  const int grp = blockIdx.z, groups = gridDim.z;
+  const float* x0 = x;   // group 0 (running statistics are updated for every group, in order, by group 0's block)
+  x += (long)grp * M * ldx; y += (long)grp * M * ldy;
+  if (add) add += (long)grp * M * ldadd;
+  if (save_mean) save_mean += (long)grp * C;
+  if (save_invstd) save_invstd += (long)grp * C;
   float mean, invstd;
   if (training) {
+    const double* wg = ws + (long)grp * 2 * C;
     const double shift = (double)__ldg(x + c);
-    const double e1 = ws[c] / (double)M, e2 = ws[C + c] / (double)M;
+    const double e1 = wg[c] / (double)M, e2 = wg[C + c] / (double)M;
     double var = e2 - e1 * e1; if (var < 0.0) var = 0.0;
     mean = (float)(shift + e1);
     invstd = (float)(1.0 / sqrt(var + (double)eps));
     if (blockIdx.y == 0 && ty == 0) {
       if (save_mean) save_mean[c] = mean;
       if (save_invstd) save_invstd[c] = invstd;
-      if (rmean) {
-        const float unbiased = (float)(M > 1 ? var * (double)M / (double)(M - 1) : var);
-        rmean[pi] = (1.f - momentum) * rmean[pi] + momentum * mean;
-        rvar[pi] = (1.f - momentum) * rvar[pi] + momentum * unbiased;
+      if (rmean && grp == 0) {
+        // momentum updates of the groups in call order (the reference runs the module once per group)
+        float rm = rmean[pi], rv = rvar[pi];
+        for (int q = 0; q < groups; ++q) {
+          const double sh = (double)__ldg(x0 + (long)q * M * ldx + c);
+          const double q1 = ws[(long)q * 2 * C + c] / (double)M, q2 = ws[(long)q * 2 * C + C + c] / (double)M;
+          double vq = q2 - q1 * q1; if (vq < 0.0) vq = 0.0;
+          const float unbiased = (float)(M > 1 ? vq * (double)M / (double)(M - 1) : vq);
+          rm = (1.f - momentum) * rm + momentum * (float)(sh + q1);
+          rv = (1.f - momentum) * rv + momentum * unbiased;
+        }
+        rmean[pi] = rm; rvar[pi] = rv;
       }
     }
   } else {
@@ -103,6 +120,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
     double* __restrict__ ws, int cb, int rpb) {
   __shared__ double r1[256];
   __shared__ double r2[256];
+  {
+    const long grp = blockIdx.z;
+    dy += grp * M * lddy; x += grp * M * ldx; save_mean += grp * C; save_invstd += grp * C; ws += grp * 2 * C;
+    if (y) y += grp * M * ldy;
+    if (dadd) dadd += grp * M * lddadd;
+  }
   const int tx = threadIdx.x % cb, ty = threadIdx.x / cb, rif = 256 / cb;
   const int c = blockIdx.x * cb + tx;
   const int mbeg = blockIdx.y * rpb;
@@ -139,13 +162,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   if (c >= C) return;
   const int pi = pmap ? pmap[c] : c;
   const int oc = cmap ? cmap[c] : c;
+  const long grp = blockIdx.z;
+  if (blockIdx.y == 0 && ty == 0 && grp == 0) {   // parameter gradients: sum over the groups, one writer
+    double sd = 0.0, sx = 0.0;
+    for (int q = 0; q < (int)gridDim.z; ++q) { sd += ws[(long)q * 2 * C + c]; sx += ws[(long)q * 2 * C + C + c]; }
+    if (dgamma) dgamma[pi] += (float)sx;
+    if (dbeta) dbeta[pi] += (float)sd;
+  }
+  dy += grp * M * lddy; x += grp * M * ldx; save_mean += grp * C; save_invstd += grp * C; ws += grp * 2 * C;
+  if (y) y += grp * M * ldy;
+  if (dx) dx += grp * M * lddx;
   const float mean = save_mean[c], invstd = save_invstd[c];
   const float g = gamma ? gamma[pi] : 1.f;
   const float sum_d = (float)ws[c], sum_dx = (float)ws[C + c];
-  if (blockIdx.y == 0 && ty == 0) {
-    if (dgamma) dgamma[pi] += sum_dx;
-    if (dbeta) dbeta[pi] += sum_d;
-  }
   if (!dx) return;
   const float k1 = training ? sum_d / (float)M : 0.f, k2 = training ? sum_dx / (float)M : 0.f;
   const float gs = g * invstd;
@@ -165,15 +194,17 @@ extern "C" int s2ag_bn_fwd(const float* x, long ldx, int M, int C, const float* 
                            const int32_t* param_map, float* running_mean, float* running_var,
                            int training, float momentum, float eps,
                            const float* add, long ldadd, float* y, long ldy, const int32_t* col_map,
-                           int act, float slope, float* save_mean, float* save_invstd, double* ws, void* stream) {
-  S2AG_CHECK_ARG(x && y && M > 0 && C > 0 && ldx >= C && ldy >= C);
+                           int act, float slope, float* save_mean, float* save_invstd, double* ws, int groups,
+                           void* stream) {
+  S2AG_CHECK_ARG(x && y && M > 0 && C > 0 && ldx >= C && ldy >= C && groups >= 1 && M % groups == 0);
   S2AG_CHECK_ARG(training ? (ws != nullptr) : (running_mean && running_var));
+  M /= groups;   // rows per statistics group
   BnGeom g = bn_geom(C);
   int colblocks = s2ag_cdiv(C, g.cb);
-  int rpb = bn_rows_per_block(M, colblocks);
-  dim3 grid(colblocks, s2ag_cdiv(M, rpb));
+  int rpb = bn_rows_per_block(M, colblocks * groups);
+  dim3 grid(colblocks, s2ag_cdiv(M, rpb), groups);
   if (training) {
-    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, (cudaStream_t)stream);
+    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C * groups, (cudaStream_t)stream);
     auto k1 = &bn_stats_kernel;
     S2AG_LAUNCH(k1, grid, 256, 0, stream, x, ldx, M, C, ws, g.cb, rpb);
   }
@@ -189,14 +220,15 @@ extern "C" int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy,
                            const float* x, long ldx, int M, int C, const float* gamma, const int32_t* param_map,
                            const float* save_mean, const float* save_invstd, int training, int act, float slope,
                            float* dx, long lddx, float* dgamma, float* dbeta, float* dadd, long lddadd,
-                           double* ws, void* stream) {
-  S2AG_CHECK_ARG(dy && x && M > 0 && C > 0 && save_mean && save_invstd && ws);
+                           double* ws, int groups, void* stream) {
+  S2AG_CHECK_ARG(dy && x && M > 0 && C > 0 && save_mean && save_invstd && ws && groups >= 1 && M % groups == 0);
   S2AG_CHECK_ARG(act == S2AG_ACT_NONE || y != nullptr);
+  M /= groups;
   BnGeom g = bn_geom(C);
   int colblocks = s2ag_cdiv(C, g.cb);
-  int rpb = bn_rows_per_block(M, colblocks);
-  dim3 grid(colblocks, s2ag_cdiv(M, rpb));
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, (cudaStream_t)stream);
+  int rpb = bn_rows_per_block(M, colblocks * groups);
+  dim3 grid(colblocks, s2ag_cdiv(M, rpb), groups);
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C * groups, (cudaStream_t)stream);
   auto k1 = &bn_bwd_reduce_kernel;
   S2AG_LAUNCH(k1, grid, 256, 0, stream, dy, lddy, y, ldy, col_map, x, ldx, M, C, save_mean, save_invstd, act, slope,
               dadd, lddadd, ws, g.cb, rpb);

@@ -55,10 +55,15 @@ extern "C" int s2ag_set_precision(int mode) {
   return S2AG_OK;
 }
 #ifndef S2AG_EMU
-namespace s2ag { int gru_debug_read_timeline(long long* host, int n); }
+namespace s2ag {
+int gru_debug_read_timeline(long long* host, int n);
+int gruc_debug_read_timeline(long long* host, int n);
+extern int g_last_gru_kernel;
+}
 #endif
 extern "C" int s2ag_debug_read_timeline(long long* host, int n) {
 #ifndef S2AG_EMU
+  if (s2ag::g_last_gru_kernel == 1) return s2ag::gruc_debug_read_timeline(host, n);
   return s2ag::gru_debug_read_timeline(host, n);
 #else
   (void)host; (void)n; return S2AG_ERR_UNSUPPORTED;

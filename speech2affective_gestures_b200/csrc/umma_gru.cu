@@ -21,6 +21,7 @@
 #include "gemm_umma.cuh"
 
 namespace s2ag {
+extern int g_last_gru_kernel;
 namespace grup {
 
 using namespace s2ag::umma;
@@ -750,6 +751,7 @@ int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const
     p.out = out; p.gates = gates; p.xchg = xchg; p.cnt = cnt;
     p.B = B; p.T = T; p.H = H; p.Kpad = kpad_of(H); p.S = S; p.nbt = nbt_all; p.bt0 = t0; p.x3 = x3;
     p.dbg = (umma::g_dbg_flags & 2) ? 1 : 0;
+    g_last_gru_kernel = 0;
     S2AG_LAUNCH(kfn, dim3(S, nbt, 2), FWD_THREADS, persist_smem_bytes(H), stream, p);
   }
   return S2AG_OK;

@@ -489,12 +489,12 @@ class AffDiscriminator(FlatParamNet):
 
     def forward_pair(self, poses_a, poses_b):
         """D(poses_a), D(poses_b) as the reference computes them back to back with the same weights
-        (processor_v2.py:808-809).  The AffEncoder runs once per input (its BatchNorm statistics are per call, in
-        call order); the GRU and the head have no cross-sample coupling, so both feature batches go through ONE
-        latency-bound recurrent launch per layer."""
-        fa = self.aff_encoder(poses_a)
-        fb = self.aff_encoder(poses_b)
-        feat = torch.cat([fa, fb], dim=0)
+        (processor_v2.py:808-809).  Nothing but BatchNorm couples the samples of a batch, so both batches go through
+        every kernel together: the AffEncoder with per-call BatchNorm statistics (two statistics groups, running
+        statistics updated in call order) and ONE latency-bound recurrent launch per GRU layer."""
+        # one pass over both stacked batches; BatchNorm keeps the two calls' statistics apart (ops.bn_groups)
+        with ops.bn_groups(2):
+            feat = self.aff_encoder(torch.cat([poses_a, poses_b], dim=0))
         g = ops.bigru(feat, _gru_param_list(self.gru), 4, self.hidden_size, self.gru.dropout, self.training)
         o = ops.dhead(g, self.out.weight, self.out.bias, self.out2.weight, self.out2.bias)
         n = poses_a.shape[0]

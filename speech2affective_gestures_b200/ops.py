@@ -236,7 +236,7 @@ def linear_t(x, w, b=None, act=ACT_NONE, slope=0.0, out=None):
 class _BnState:
     """The per-call record a BN forward leaves for its backward."""
     __slots__ = ("x", "ldx", "M", "C", "mean", "invstd", "training", "act", "slope", "y", "ldy", "cmap", "pmap",
-                 "want_w")
+                 "want_w", "groups")
 
 
 _bn_repeat = [1]
@@ -268,33 +268,55 @@ class bn_repeat:
         _bn_repeat[0] = self.prev
 
 
+_bn_groups = [1]
+
+
+class bn_groups:
+    """Context: every BatchNorm forward inside it sees `n` consecutive, equally sized, INDEPENDENT batches stacked
+    along the leading dimension -- what the reference computes as n successive calls of the same module
+    (processor_v2.py:808-809: D(target), D(out.detach())).  Statistics are per group; the running statistics get the
+    groups' momentum updates in call order.  All other kernels are per-sample, so stacking is otherwise invisible."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        self.prev = _bn_groups[0]
+        _bn_groups[0] = self.n
+
+    def __exit__(self, *a):
+        _bn_groups[0] = self.prev
+
+
 def _bn_forward(x2, ldx, M, C, bn, training, act, slope, y2, ldy, add2=None, ldadd=0, cmap=None, pmap=None):
     """x2/y2: row views. bn: module-like with weight,bias,running_mean,running_var,momentum,eps."""
-    mean = _empty((C,), x2)
-    invstd = _empty((C,), x2)
-    ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    groups = _bn_groups[0]
+    mean = _empty((groups * C,), x2)
+    invstd = _empty((groups * C,), x2)
+    ws = torch.empty(2 * C * groups, dtype=torch.float64, device=x2.device)
     rep = _bn_repeat[0] if training else 1
     momentum = float(bn.momentum) if rep == 1 else 1.0 - (1.0 - float(bn.momentum)) ** rep
     _C.call("s2ag_bn_fwd", _p(x2), ldx, M, C, _p(bn.weight), _p(bn.bias), _p(pmap), _p(bn.running_mean),
             _p(bn.running_var), 1 if training else 0, momentum, float(bn.eps), _p(add2), ldadd, _p(y2), ldy,
-            _p(cmap), act, float(slope), _p(mean), _p(invstd), _p(ws), _stream(x2))
+            _p(cmap), act, float(slope), _p(mean), _p(invstd), _p(ws), groups, _stream(x2))
     if training:
-        bn._s2ag_batches = getattr(bn, "_s2ag_batches", 0) + rep
+        bn._s2ag_batches = getattr(bn, "_s2ag_batches", 0) + rep * groups
     s = _BnState()
     s.x, s.ldx, s.M, s.C, s.mean, s.invstd, s.training = x2, ldx, M, C, mean, invstd, training
     s.act, s.slope, s.y, s.ldy, s.cmap, s.pmap = act, float(slope), y2, ldy, cmap, pmap
     s.want_w = bn.weight.requires_grad
+    s.groups = groups
     return s
 
 
 def _bn_backward(s, bn, dy2, lddy, need_dx=True, dadd2=None, lddadd=0):
-    ws = torch.empty(2 * s.C, dtype=torch.float64, device=dy2.device)
+    ws = torch.empty(2 * s.C * s.groups, dtype=torch.float64, device=dy2.device)
     dx = _empty((s.M, s.C), dy2) if need_dx else None
     wg = s.want_w
     _C.call("s2ag_bn_bwd", _p(dy2), lddy, _p(s.y), s.ldy, _p(s.cmap), _p(s.x), s.ldx, s.M, s.C, _p(bn.weight),
             _p(s.pmap), _p(s.mean), _p(s.invstd), 1 if s.training else 0, s.act, s.slope, _p(dx), s.C,
             _p(_grad_of(bn.weight)) if wg else None, _p(_grad_of(bn.bias)) if wg else None, _p(dadd2), lddadd,
-            _p(ws), _stream(dy2))
+            _p(ws), s.groups, _stream(dy2))
     return dx
 
 

@@ -159,6 +159,33 @@ def test_bn_maps_add(dev, training):
     close(bn2.running_mean, bn.running_mean, what="rm"); close(bn2.running_var, bn.running_var, what="rv")
 
 
+def test_bn_groups_equal_successive_calls(dev):
+    """ops.bn_groups(2) over two stacked batches == two successive calls of the same BatchNorm (processor_v2.py:808-809:
+    D(target) then D(out)): outputs, input / parameter gradients, running statistics and batch counter"""
+    torch.manual_seed(14)
+    M, C = 200, 24
+    bn = nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+    import copy
+    bn2 = copy.deepcopy(bn).to(dev)
+    xa, xb = torch.randn(M, C) * 2 + 1, torch.randn(M, C) * 0.5 - 3
+    ga, gb = torch.randn(M, C), torch.randn(M, C)
+    ra, rb = P(xa, "cpu"), P(xb, "cpu")
+    ya = F.leaky_relu(bn(ra.unsqueeze(-1)).squeeze(-1), 0.3)
+    yb = F.leaky_relu(bn(rb.unsqueeze(-1)).squeeze(-1), 0.3)
+    torch.autograd.backward([ya, yb], [ga, gb])
+    xs = P(torch.cat([xa, xb]), dev)
+    with ops.bn_groups(2):
+        y = ops.bn_act(xs, bn2, ops.ACT_LEAKY, 0.3)
+    y.backward(torch.cat([ga, gb]).to(dev))
+    close(y, torch.cat([ya, yb]), what="y")
+    close(xs.grad, torch.cat([ra.grad, rb.grad]), what="dx")
+    close(bn2.weight.grad, bn.weight.grad, what="dgamma"); close(bn2.bias.grad, bn.bias.grad, what="dbeta")
+    close(bn2.running_mean, bn.running_mean, what="rm"); close(bn2.running_var, bn.running_var, what="rv")
+    assert bn2._s2ag_batches == 2
+
+
 def test_bn_large_mean(dev):
     """statistics must survive |mean| >> std (shifted accumulation)"""
     torch.manual_seed(5)

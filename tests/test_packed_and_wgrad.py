@@ -111,10 +111,11 @@ def test_conv_wgrad_shift_kernel(N, H, W, Cin, Cout, KH, KW, ph, pw):
     assert _rel(db_shift, dy.double().sum((0, 1, 2))) < 1e-5
 
 
-@pytest.mark.parametrize("In,H,B", [(8, 64, 200), (24, 40, 5)])
-def test_cta_local_gru_experiment_matches_slice_parallel_kernels(In, H, B):
-    """umma_gru_local.cu (opt-in, s2ag_debug_flags bit 9; measured slower, see its header): same results as the
-    default slice-parallel persistent kernels, forward output and every gradient."""
+@pytest.mark.parametrize("In,H,B", [(8, 64, 200), (24, 40, 5), (88, 300, 70), (16, 24, 33)])
+def test_cluster_gru_forward_matches_l2_exchange_kernel(In, H, B):
+    """umma_gru_cluster.cu (thread-block clusters exchanging h through distributed shared memory; default for H <= 80,
+    s2ag_debug_flags bit 2048 forces it for every size) against umma_gru.cu (bit 1024): forward output and every
+    gradient (the saved gates feed the shared BPTT kernel), ragged clip tiles and partial last slices included."""
     dev = torch.device("cuda:0")
     lib = _C.lib()
     T, L = 34, 2
@@ -124,7 +125,7 @@ def test_cta_local_gru_experiment_matches_slice_parallel_kernels(In, H, B):
     x0 = torch.randn(B, T, In, generator=g)
     gy = torch.randn(B, T, 2 * H, generator=g).to(dev)
     res = {}
-    for name, flags in (("slices", 0), ("local", 512)):
+    for name, flags in (("l2", 1024), ("cluster", 2048)):
         lib.s2ag_debug_flags(flags)
         try:
             ps = [t.clone().to(dev).requires_grad_(True) for t in ps0]
@@ -135,5 +136,5 @@ def test_cta_local_gru_experiment_matches_slice_parallel_kernels(In, H, B):
             res[name] = [y.detach()] + [q.grad for q in ps]
         finally:
             lib.s2ag_debug_flags(0)
-    for a, b in zip(res["local"], res["slices"]):
+    for a, b in zip(res["cluster"], res["l2"]):
         assert _rel(a, b) < 2e-5, _rel(a, b)

@@ -40,6 +40,8 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     pr.replay_step()
     torch.cuda.synchronize()
+if os.environ.get("S2AG_TRACE"):
+    prof.export_chrome_trace(os.environ["S2AG_TRACE"])
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
 ks = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "device_index", 0)) for e in evs))
 if not ks:
