@@ -61,6 +61,8 @@ int s2ag_debug_flags(int flags);
 /* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
  * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */
 int s2ag_debug_read_timeline(long long* host, int n);
+/* bring-up aid: number of co-resident clusters of the cluster GRU forward (backward = 0) / BPTT (1) kernel for hidden size H */
+int s2ag_debug_gru_cluster_occupancy(int H, int backward);
 
 #define S2AG_ACT_NONE 0
 #define S2AG_ACT_RELU 1

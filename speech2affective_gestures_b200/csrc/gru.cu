@@ -20,6 +20,11 @@ bool gru_persist_supported(int H);
 bool gru_cluster_supported(int H);
 int gru_cluster_fwd(const float* gi, const float* whh_f, long whh_dstride, const float* bhh_f, long bhh_dstride, float* out,
                     float* gates, int B, int T, int H, int x3, void* stream);
+bool gru_cluster_fwd_selected(int H, int B);
+bool gru_cluster_bwd_selected(int H, int B);
+int gru_cluster_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
+                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, int B, int T, int H, int x3,
+                    void* stream);
 size_t gru_persist_ws_bytes(int B, int H);
 int gru_persist_fwd(const float* gi, const float* whh_f, long whh_dstride, const float* bhh_f, long bhh_dstride,
                     float* out, float* gates, void* ws, int B, int T, int H, int x3, void* stream);
@@ -168,7 +173,7 @@ extern "C" int s2ag_gru_layer_fwd(const float* x, long ldx, const float* w_ih_f,
     launch_gemm(a, b, e, M, 3 * H, In, 2, 1, stream);
   }
 #ifndef S2AG_EMU
-  if (g_engine == 0 && gru_cluster_supported(H)) {
+  if (g_engine == 0 && gru_cluster_fwd_selected(H, B)) {
     // one launch for all T steps of both directions: clusters of slice CTAs exchanging h through DSMEM
     int rc = gru_cluster_fwd(gi_ws, w_hh_f, (long)(w_hh_r - w_hh_f), b_hh_f, (long)(b_hh_r - b_hh_f), out, gates, B, T, H,
                              umma::g_precision == 0 ? 1 : 0, stream);
@@ -200,7 +205,7 @@ extern "C" int s2ag_gru_recurrence_fwd(const float* gi_ws, const float* w_hh_f, 
                                        const float* b_hh_r, float* out, float* gates, int B, int T, int H, void* stream) {
   S2AG_CHECK_ARG(gi_ws && w_hh_f && w_hh_r && b_hh_f && b_hh_r && out && B > 0 && T > 0 && H > 0);
 #ifndef S2AG_EMU
-  if (g_engine == 0 && gru_cluster_supported(H)) {
+  if (g_engine == 0 && gru_cluster_fwd_selected(H, B)) {
     int rc = gru_cluster_fwd(gi_ws, w_hh_f, (long)(w_hh_r - w_hh_f), b_hh_f, (long)(b_hh_r - b_hh_f), out, gates, B, T, H,
                              umma::g_precision == 0 ? 1 : 0, stream);
     if (rc != S2AG_OK) { s2ag_set_error("gru_cluster_fwd failed (%d)", rc); return rc; }
@@ -247,7 +252,12 @@ extern "C" int s2ag_gru_layer_bwd(const float* dout, long lddout, int dir_stride
   auto kg = &gru_bwd_gate_kernel;
   bool persistent = false;
 #ifndef S2AG_EMU
-  if (do_rec && g_engine == 0 && gru_persist_bwd_ws_bytes(B, H) > 0) {
+  if (do_rec && g_engine == 0 && gru_cluster_bwd_selected(H, B)) {
+    int rc = gru_cluster_bwd(dout, lddout, dir_stride, out, gates, w_hh_f, (long)(w_hh_r - w_hh_f), dgi, dgh, B, T, H,
+                             umma::g_precision == 0 ? 1 : 0, stream);
+    if (rc != S2AG_OK) { s2ag_set_error("gru_cluster_bwd failed (%d)", rc); return rc; }
+    persistent = true;
+  } else if (do_rec && g_engine == 0 && gru_persist_bwd_ws_bytes(B, H) > 0) {
     int rc = gru_persist_bwd(dout, lddout, dir_stride, out, gates, w_hh_f, (long)(w_hh_r - w_hh_f), dgi, dgh,
                              carry[0] + 4L * B * H, B, T, H, umma::g_precision == 0 ? 1 : 0, stream);
     if (rc != S2AG_OK) { s2ag_set_error("gru_persist_bwd failed (%d)", rc); return rc; }

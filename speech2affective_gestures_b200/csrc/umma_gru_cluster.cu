@@ -460,6 +460,297 @@ __global__ void __launch_bounds__(THREADS, 1) gru_cluster_fwd_kernel(Params p) {
   if (warp == 0) tmem_dealloc(tmem_base, NACC * 2 * CN);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// BPTT in the same cluster decomposition (cluster = S slice CTAs of one tile of CN clips and one direction).
+// Per step (forward order reversed) a CTA computes the gate gradients of its U units from the saved gates,
+//   dh = dout + carry;  dn = dh(1-z)(1-n^2);  dz = dh(h_prev - n) z(1-z);  dr = dn*ghn*r(1-r),
+// writes dgi = (dr,dz,dn) and dgh = (dr,dz,dn*r) rows for the time-batched weight-gradient GEMMs, and contributes
+//   partial[k, clip] = sum_{c in its 3U gate rows} W_hh[c, k] * dgh[clip, c]        for ALL units k
+// on tcgen05: A = W_slice^T (rows k, K = own gate rows c; bf16 hi/lo, stationary), B = its own dgh^T (MN-major,
+// [hi clips | lo clips] x c: no operand exchange at all), accumulators [128 rows x 64 columns] per 128-row tile of k
+// (the last tile overlaps its predecessor instead of padding: 320 = 128 + 128 + 64).  The partials are
+// reduce-scattered through DISTRIBUTED SHARED MEMORY: every thread stores the 16 clips of its row k straight from the
+// TMEM load into the receive slot [source CTA][unit][clip] of the CTA that owns unit k (st.shared::cluster.v4), one
+// release.cluster arrival per (source, destination) pair and step; the owner sums its S slots:
+//   carry[clip, j] = dh*z + sum_src slot[src][j][clip].
+// umma_gru.cu exchanges the same partials through L2 as 164 KB of sector stores + 155 KB of sector loads per CTA and
+// step behind gpu-scope release/acquire (22.5 k cycles per step at H = 300); here a CTA sends and receives 40 KB.
+struct BwdParams {
+  const float* dout; long lddout; int dir_stride;
+  const float* out;         // [B][T][2H] forward output (h_prev)
+  const float* gates;       // [T][2][4][H][B]
+  const float* whh; long whh_dstride;
+  float* dgi;               // [B*T][2][3H]
+  float* dgh;               // [B*T][2][3H]
+  int B, T, H, Kpad, S, U, Kc, x3;
+  int dbg;
+};
+#define GRUB_MARK(slot) do { if (dbg) g_gruc_timeline[(step & 63) * 16 + (slot)] = clock64(); } while (0)
+
+constexpr int BW_WORKERS = 256, BW_THREADS = BW_WORKERS + 32;
+
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_m(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// shared-memory map: [0, HDR) mbarriers: mma_done @0, b_full @8, rx_full @16, credit @24; TMEM slot @128
+//   a_hi, a_lo   W_slice^T, K-major [Kc/8][AR rows k][16 B] each (AR = max(Kpad, 128); element (k, c) = W_hh[row(c)][k])
+//   b_op         dgh^T, MN-major [cg: 0-3 hi clips, 4-7 lo clips][c (Kc)][16 B]
+//   rx           [source CTA (S)][unit (U)][CN clips] fp32
+__global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad, S = p.S, U = p.U, Kc = p.Kc;
+  const int slice = (int)cluster_ctarank(), tile = blockIdx.y, dir = blockIdx.z;
+  const int AR = Kpad < 128 ? 128 : Kpad;
+  const int ntiles = (Kpad + 127) >> 7;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mma_done = sbase, b_full = sbase + 8, rx_full = sbase + 16, credit = sbase + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
+  const int a_half = (Kc >> 3) * AR * 16;
+  unsigned char* a_hi = smem + HDR;
+  unsigned char* a_lo = a_hi + a_half;
+  unsigned char* b_op = a_lo + a_half;
+  float* rx = reinterpret_cast<float*>(b_op + 8 * Kc * 16);
+
+  if (tid == 0) {
+    mbar_init(mma_done, 1);
+    mbar_init(b_full, BW_WORKERS / 32);
+    mbar_init(rx_full, (uint32_t)S);
+    mbar_init(credit, (uint32_t)S);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(sbase + 128, 256);
+
+  // ---- stationary A operand: element (row k, c) = W_hh[g*H + j][k] with c = g*U + u, j = slice*U + u
+  const float* whh = p.whh + dir * p.whh_dstride;
+  for (int idx = tid; idx < (Kc >> 3) * AR; idx += BW_THREADS) {
+    const int k = idx % AR, kc = idx / AR;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = kc * 8 + i, g = c / U, u = c - g * U, j = slice * U + u;
+      v[i] = (g < 3 && j < H && k < H) ? __ldg(whh + ((long)g * H + j) * H + k) : 0.f;
+    }
+    split_store(v, a_hi, a_lo, (kc * AR + k) * 16, true);
+  }
+  for (int idx = tid; idx < (8 * Kc * 16) / 16; idx += BW_THREADS) reinterpret_cast<uint4*>(b_op)[idx] = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();
+
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const bool dbg_cta = p.dbg && slice == 0 && tile == 0 && dir == 0;
+  if (warp_u == BW_WORKERS / 32) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const bool dbg = dbg_cta;
+      const uint32_t idesc64 = make_idesc_m(128, 2 * CN) | (1u << 16), idesc32 = make_idesc_m(128, CN) | (1u << 16);
+      const uint32_t a_lbo = (uint32_t)AR * 16;
+      const uint32_t bb = smem_u32(b_op), b_sbo = (uint32_t)Kc * 16;
+      const int ksteps = Kc >> 4;
+      for (int step = 0; step + 1 < T; ++step) {
+        mbar_wait(b_full, (uint32_t)(step & 1));      // dgh operand of this step staged by the 8 worker warps
+        tc_fence_after();
+        GRUB_MARK(10);
+        for (int m = 0; m < ntiles; ++m) {
+          int row0 = 128 * m; if (row0 + 128 > AR) row0 = AR - 128;
+          const uint64_t dah0 = make_desc(smem_u32(a_hi) + (uint32_t)row0 * 16, a_lbo, 128);
+          const uint64_t dal0 = make_desc(smem_u32(a_lo) + (uint32_t)row0 * 16, a_lbo, 128);
+          const uint32_t d = tmem_base + (uint32_t)(m * 2 * CN);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t aoff = (uint64_t)(ks * ((2 * a_lbo) >> 4));
+            const uint64_t db = make_desc(bb + (uint32_t)(ks * 16 * 16), 128, b_sbo);
+            if (p.x3) {
+              mma_bf16(d, dah0 + aoff, db, idesc64, ks > 0 ? 1u : 0u);   // [W_hi dgh_hi | W_hi dgh_lo]
+              mma_bf16(d, dal0 + aoff, db, idesc32, 1u);                 // + W_lo dgh_hi
+            } else {
+              mma_bf16(d, dah0 + aoff, db, idesc32, ks > 0 ? 1u : 0u);
+            }
+          }
+        }
+        mma_commit(mma_done);
+        GRUB_MARK(11);
+      }
+    }
+  } else {
+    // ================================ workers ================================
+    // phase A (gate gradients): thread = (unit u of the slice, group of 8 clips); lanes run along the units, so the
+    // dout / h_prev loads and the dgi / dgh stores are contiguous along j
+    const int ga_u = tid % U, ga_cg = tid / U;
+    const bool ga_on = tid < 4 * U;
+    const int j = slice * U + ga_u;
+    const bool j_ok = ga_on && j < H;
+    const int bA = tile * CN + ga_cg * 8;
+    // phase B (reduce-scatter): thread = (row k of a 128-row tile, 16 clips)
+    const int q = warp & 3, half = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+    const uint32_t rx_base = smem_u32(rx);
+    float carry[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) carry[i] = 0.f;
+    const bool dbg = dbg_cta && tid == 0;
+    const bool gvec = (B & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gates) & 15) == 0 && bA + 8 <= B;
+
+    for (int step = 0; step < T; ++step) {
+      const int fs = T - 1 - step;                         // forward step being differentiated
+      const int t = dir == 0 ? fs : T - 1 - fs;
+      const int tprev = dir == 0 ? t - 1 : t + 1;
+      GRUB_MARK(0);
+      // ---- operands of this step (independent of the recurrence)
+      float dh[8], hp[8], r[8], z[8], n[8], ghn[8];
+      if (j_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = bA + i;
+          const bool ok = b < B;
+          const long rowi = (long)(ok ? b : 0) * T + t;
+          dh[i] = ok ? __ldg(p.dout + rowi * p.lddout + (long)dir * p.dir_stride + j) : 0.f;
+          hp[i] = (ok && fs > 0) ? __ldg(p.out + ((long)b * T + tprev) * 2 * H + (long)dir * H + j) : 0.f;
+        }
+        const float* gs = p.gates + ((((long)t * 2 + dir) * 4) * H + j) * B + bA;
+        const long gstride = (long)H * B;
+        if (gvec) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(gs)), r1 = __ldg(reinterpret_cast<const float4*>(gs) + 1);
+          const float4 z0 = __ldg(reinterpret_cast<const float4*>(gs + gstride)), z1 = __ldg(reinterpret_cast<const float4*>(gs + gstride) + 1);
+          const float4 n0 = __ldg(reinterpret_cast<const float4*>(gs + 2 * gstride)), n1 = __ldg(reinterpret_cast<const float4*>(gs + 2 * gstride) + 1);
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(gs + 3 * gstride)), h1 = __ldg(reinterpret_cast<const float4*>(gs + 3 * gstride) + 1);
+          r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+          z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+          n[0] = n0.x; n[1] = n0.y; n[2] = n0.z; n[3] = n0.w; n[4] = n1.x; n[5] = n1.y; n[6] = n1.z; n[7] = n1.w;
+          ghn[0] = h0.x; ghn[1] = h0.y; ghn[2] = h0.z; ghn[3] = h0.w; ghn[4] = h1.x; ghn[5] = h1.y; ghn[6] = h1.z; ghn[7] = h1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = bA + i < B;
+            r[i] = ok ? __ldg(gs + i) : 0.f; z[i] = ok ? __ldg(gs + gstride + i) : 0.f;
+            n[i] = ok ? __ldg(gs + 2 * gstride + i) : 0.f; ghn[i] = ok ? __ldg(gs + 3 * gstride + i) : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dh[i] = hp[i] = r[i] = z[i] = n[i] = ghn[i] = 0.f;
+      }
+      GRUB_MARK(1);
+      // ---- carry of the previous step: sum of the S partial slots (written by every CTA of the cluster)
+      if (step > 0) {
+        mbar_wait_cluster(rx_full, (uint32_t)((step - 1) & 1));
+        GRUB_MARK(2);
+        if (ga_on) {
+#pragma unroll 2
+          for (int src = 0; src < S; ++src) {
+            const float4* sp = reinterpret_cast<const float4*>(rx + ((size_t)src * U + ga_u) * CN + ga_cg * 8);
+            const float4 a = sp[0], b4 = sp[1];
+            carry[0] += a.x; carry[1] += a.y; carry[2] += a.z; carry[3] += a.w;
+            carry[4] += b4.x; carry[5] += b4.y; carry[6] += b4.z; carry[7] += b4.w;
+          }
+        }
+        // the slots may be overwritten once every worker has read them: credit to every CTA of the cluster
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && lane < S && fs > 0) mbar_arrive_remote(mapa(credit, (uint32_t)lane));
+        GRUB_MARK(3);
+      }
+      float dr[8], dz[8], dn[8], dnr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dh[i] += carry[i];
+        dn[i] = dh[i] * (1.f - z[i]) * (1.f - n[i] * n[i]);
+        dz[i] = dh[i] * (hp[i] - n[i]) * z[i] * (1.f - z[i]);
+        dr[i] = dn[i] * ghn[i] * r[i] * (1.f - r[i]);
+        dnr[i] = dn[i] * r[i];
+        carry[i] = dh[i] * z[i];
+      }
+      if (fs > 0) {
+        // ---- B operand: rows c = g*U + u of this unit, 8 clips = one 16-byte chunk per plane
+        if (ga_on) {
+          const float* src3[3] = {dr, dz, dnr};
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = src3[g][2 * e], x1 = src3[g][2 * e + 1];
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+              lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            const int c = g * U + ga_u;
+            *reinterpret_cast<uint4*>(b_op + ((ga_cg * Kc) + c) * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(b_op + (((4 + ga_cg) * Kc) + c) * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(b_full);
+      }
+      GRUB_MARK(4);
+      // ---- dgi / dgh rows for the time-batched weight-gradient GEMMs (while the tensor core works)
+      if (j_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = bA + i;
+          if (b < B) {
+            float* a = p.dgi + (((long)b * T + t) * 2 + dir) * 3 * H + j;
+            float* c = p.dgh + (((long)b * T + t) * 2 + dir) * 3 * H + j;
+            a[0] = dr[i]; a[H] = dz[i]; a[2 * H] = dn[i];
+            c[0] = dr[i]; c[H] = dz[i]; c[2 * H] = dnr[i];
+          }
+        }
+      }
+      GRUB_MARK(5);
+      if (fs > 0) {
+        // ---- partial products of this CTA's gate rows for EVERY unit k: TMEM -> the owner's receive slot
+        mbar_wait(mma_done, (uint32_t)(step & 1));
+        GRUB_MARK(6);
+        tc_fence_after();
+        if (step > 0 && warp == 0 && lane == 0) mbar_wait(credit, (uint32_t)((step - 1) & 1));
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // every peer has consumed the previous partials
+        GRUB_MARK(7);
+        for (int m = 0; m < ntiles; ++m) {
+          int row0 = 128 * m; if (row0 + 128 > AR) row0 = AR - 128;
+          const int k = row0 + 32 * q + lane;
+          float v[16];
+          tmem_ld16_nowait(t_lane + (uint32_t)(m * 2 * CN), v);
+          if (p.x3) {
+            float w[16];
+            tmem_ld16_nowait(t_lane + (uint32_t)(m * 2 * CN + CN), w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+          if (k >= 128 * m && k < S * U) {   // (rows below 128 m were delivered by the previous, overlapping tile)
+            const int d = k / U, ul = k - d * U;
+            const uint32_t dst = mapa(rx_base + (uint32_t)((((slice * U) + ul) * CN + half * 16) * 4), (uint32_t)d);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) st_cluster_v4(dst + (uint32_t)(i * 4), v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        tc_fence_before();
+        GRUB_MARK(8);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // one release.cluster arrival per destination: cumulative over the barrier above (all 8 warps' DSMEM stores)
+        if (warp == 0 && lane < S) mbar_arrive_remote_release(mapa(rx_full, (uint32_t)lane));
+        GRUB_MARK(9);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+static inline int kc_of(int U) { return (3 * U + 15) / 16 * 16; }
+
 static inline int slices_of(int H) { int s = (H + 39) / 40; return s < 1 ? 1 : s; }
 static inline int units_of(int H) { const int S = slices_of(H); return ((H + S - 1) / S + 7) / 8 * 8; }
 static inline int kpad_of(int H) { return (slices_of(H) * units_of(H) + 15) / 16 * 16; }
@@ -468,6 +759,11 @@ static inline size_t smem_bytes(int H) {
   return HDR + (size_t)2 * nchunk * 128 * 16 + (size_t)(slices_of(H) + 1) * blk + (size_t)2 * blk;
 }
 static inline size_t tile_bytes(int H) { return (size_t)2 * (128 + 2 * units_of(H)) * 33 * sizeof(float); }
+
+static inline size_t bwd_smem_bytes(int H) {
+  const int U = units_of(H), Kc = kc_of(U), Kpad = kpad_of(H), AR = Kpad < 128 ? 128 : Kpad;
+  return HDR + (size_t)2 * (Kc / 8) * AR * 16 + (size_t)8 * Kc * 16 + (size_t)slices_of(H) * U * CN * sizeof(float);
+}
 
 }  // namespace gruc
 
@@ -520,3 +816,87 @@ int gru_cluster_fwd(const float* gi, const float* whh_f, long whh_dstride, const
 }
 
 }  // namespace s2ag
+
+extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward);
+namespace s2ag {
+// Clusters are gang-scheduled and independent, so more clusters than fit simply run in waves -- but a second wave
+// doubles the time of a latency-bound recurrence.  Measured on B200: 15 clusters of 8 CTAs (H = 300) are co-resident,
+// one short of the 16 that 256 clips x 2 directions need; 74 clusters of 2 CTAs (H = 64).  The cluster kernels are
+// therefore selected only when the whole launch is one wave (the L2-exchange kernels of umma_gru.cu otherwise).
+static bool one_wave(int H, int B, int backward) {
+  static int cache[2][512];
+  if (H >= 512) return false;
+  if (cache[backward][H] == 0) {
+    const int n = s2ag_debug_gru_cluster_occupancy(H, backward);
+    cache[backward][H] = n > 0 ? n : -1;
+  }
+  return 2 * ((B + gruc::CN - 1) / gruc::CN) <= cache[backward][H];
+}
+bool gru_cluster_fwd_selected(int H, int B) {
+  if (!gru_cluster_supported(H)) return false;
+  return (umma::g_dbg_flags & 2048) != 0 || one_wave(H, B, 0);
+}
+bool gru_cluster_bwd_supported(int H) {
+  if (umma::g_dbg_flags & 8192) return false;   // A/B switch: the L2-exchange BPTT kernel of umma_gru.cu
+  return H >= 8 && gruc::slices_of(H) <= gruc::MAXS && gruc::units_of(H) <= 40 && gruc::kpad_of(H) <= 384 &&
+         gruc::bwd_smem_bytes(H) <= 227 * 1024;
+}
+bool gru_cluster_bwd_selected(int H, int B) {
+  if (!gru_cluster_bwd_supported(H)) return false;
+  return (umma::g_dbg_flags & 2048) != 0 || one_wave(H, B, 1);
+}
+
+int gru_cluster_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
+                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, int B, int T, int H, int x3,
+                    void* stream) {
+  using namespace gruc;
+  if (!gru_cluster_bwd_supported(H)) return S2AG_ERR_UNSUPPORTED;
+  auto kfn = &gru_cluster_bwd_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2AG_ERR_LAUNCH;
+    attr_set = true;
+  }
+  BwdParams p;
+  p.dout = dout; p.lddout = lddout; p.dir_stride = dir_stride; p.out = out; p.gates = gates;
+  p.whh = whh_f; p.whh_dstride = whh_dstride; p.dgi = dgi; p.dgh = dgh;
+  p.B = B; p.T = T; p.H = H; p.S = slices_of(H); p.U = units_of(H); p.Kpad = kpad_of(H); p.Kc = kc_of(p.U); p.x3 = x3;
+  p.dbg = (umma::g_dbg_flags & 8) ? 1 : 0;
+  g_last_gru_kernel = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.S, (B + CN - 1) / CN, 2);
+  cfg.blockDim = dim3(gruc::BW_THREADS);
+  cfg.dynamicSmemBytes = gruc::bwd_smem_bytes(H);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  ++g_s2ag_launches;
+  if (cudaLaunchKernelEx(&cfg, kfn, p) != cudaSuccess) return S2AG_ERR_LAUNCH;
+  return S2AG_OK;
+}
+}  // namespace s2ag
+
+// bring-up aid: how many clusters of the forward / BPTT kernel can be co-resident (cudaOccupancyMaxActiveClusters)
+extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward) {
+  using namespace s2ag::gruc;
+  cudaLaunchConfig_t cfg = {};
+  const int S = slices_of(H);
+  cfg.gridDim = dim3(S, 64, 2);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = -1;
+  if (backward) {
+    cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = bwd_smem_bytes(H);
+    cudaFuncSetAttribute(gru_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_bwd_kernel, &cfg) != cudaSuccess) return -1;
+  } else {
+    cfg.blockDim = dim3(s2ag::gruc::THREADS); cfg.dynamicSmemBytes = s2ag::gruc::smem_bytes(H);
+    cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_fwd_kernel, &cfg) != cudaSuccess) return -1;
+  }
+  return n;
+}

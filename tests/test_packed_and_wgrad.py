@@ -112,20 +112,24 @@ def test_conv_wgrad_shift_kernel(N, H, W, Cin, Cout, KH, KW, ph, pw):
 
 
 @pytest.mark.parametrize("In,H,B", [(8, 64, 200), (24, 40, 5), (88, 300, 70), (16, 24, 33)])
-def test_cluster_gru_forward_matches_l2_exchange_kernel(In, H, B):
-    """umma_gru_cluster.cu (thread-block clusters exchanging h through distributed shared memory; default for H <= 80,
-    s2ag_debug_flags bit 2048 forces it for every size) against umma_gru.cu (bit 1024): forward output and every
-    gradient (the saved gates feed the shared BPTT kernel), ragged clip tiles and partial last slices included."""
+def test_cluster_gru_kernels_match_l2_exchange_kernels(In, H, B):
+    """umma_gru_cluster.cu (thread-block clusters exchanging h / reduce-scattering the BPTT partials through
+    distributed shared memory; forward default for H <= 80, s2ag_debug_flags bit 2048 forces it for every size)
+    against the L2-exchange kernels of umma_gru.cu (bits 1024 | 8192): forward output and every gradient, ragged clip
+    tiles and partial last slices included."""
     dev = torch.device("cuda:0")
     lib = _C.lib()
     T, L = 34, 2
     g = torch.Generator().manual_seed(In + H)
-    ps0 = [torch.randn(s, generator=g) * 0.2 for l in range(L) for s in
+    # (weights ~ 1/sqrt(H) like nn.GRU's init: larger weights make the recurrence chaotic and any two fp32-grade
+    # implementations drift apart -- both kernels are then 6e-4 from an fp64 nn.GRU at H = 300)
+    sc = 0.2 if H <= 64 else 0.05
+    ps0 = [torch.randn(s, generator=g) * sc for l in range(L) for s in
            [(3 * H, In if l == 0 else 2 * H), (3 * H, H), (3 * H,), (3 * H,)] * 2]
     x0 = torch.randn(B, T, In, generator=g)
     gy = torch.randn(B, T, 2 * H, generator=g).to(dev)
     res = {}
-    for name, flags in (("l2", 1024), ("cluster", 2048)):
+    for name, flags in (("l2", 1024 | 8192), ("cluster", 2048)):
         lib.s2ag_debug_flags(flags)
         try:
             ps = [t.clone().to(dev).requires_grad_(True) for t in ps0]
