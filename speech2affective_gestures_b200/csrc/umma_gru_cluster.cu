@@ -482,7 +482,7 @@ struct BwdParams {
   const float* whh; long whh_dstride;
   float* dgi;               // [B*T][2][3H]
   float* dgh;               // [B*T][2][3H]
-  int B, T, H, Kpad, S, U, Kc, x3;
+  int B, T, H, Kpad, S, U, Kc, AR, x3;
   int dbg;
 };
 #define GRUB_MARK(slot) do { if (dbg) g_gruc_timeline[(step & 63) * 16 + (slot)] = clock64(); } while (0)
@@ -501,15 +501,20 @@ __device__ __forceinline__ uint32_t make_idesc_m(int m, int n) {
 
 // shared-memory map: [0, HDR) mbarriers: mma_done @0, b_full @8, rx_full @16, credit @24; TMEM slot @128
 //   a_hi, a_lo   W_slice^T, K-major [Kc/8][AR rows k][16 B] each (AR = max(Kpad, 128); element (k, c) = W_hh[row(c)][k])
-//   b_op         dgh^T, MN-major [cg: 0-3 hi clips, 4-7 lo clips][c (Kc)][16 B]
-//   rx           [source CTA (S)][unit (U)][CN clips] fp32
+//   b_op         dgh^T, MN-major [clip group of 8: NG hi groups, then NG lo groups][c (Kc)][16 B]
+//   rx           [source CTA (S)][unit (U)][BCN clips] fp32
+// BCN = clips per cluster: 32, or 40 when that makes the launch ONE wave (256 clips x 2 directions = 14 clusters of
+// 8 CTAs instead of 16; 15 are co-resident).  With BCN = 40 the second MMA of a k-step has N = 48: its extra 8 columns
+// add W_lo * dgh_lo of clips 0-7 to their hi*lo columns, a (valid) fourth-order term.
+template <int BCN>
 __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParams p) {
+  constexpr int NG = BCN / 8, N2 = (BCN + 15) / 16 * 16;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, T = p.T, B = p.B, Kpad = p.Kpad, S = p.S, U = p.U, Kc = p.Kc;
   const int slice = (int)cluster_ctarank(), tile = blockIdx.y, dir = blockIdx.z;
-  const int AR = Kpad < 128 ? 128 : Kpad;
-  const int ntiles = (Kpad + 127) >> 7;
+  const int AR = p.AR;                       // rows of A: the real units rounded up to 8 (>= 128)
+  const int ntiles = (AR + 127) >> 7;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t mma_done = sbase, b_full = sbase + 8, rx_full = sbase + 16, credit = sbase + 24;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
   unsigned char* a_hi = smem + HDR;
   unsigned char* a_lo = a_hi + a_half;
   unsigned char* b_op = a_lo + a_half;
-  float* rx = reinterpret_cast<float*>(b_op + 8 * Kc * 16);
+  float* rx = reinterpret_cast<float*>(b_op + 2 * NG * Kc * 16);
 
   if (tid == 0) {
     mbar_init(mma_done, 1);
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
     }
     split_store(v, a_hi, a_lo, (kc * AR + k) * 16, true);
   }
-  for (int idx = tid; idx < (8 * Kc * 16) / 16; idx += BW_THREADS) reinterpret_cast<uint4*>(b_op)[idx] = make_uint4(0, 0, 0, 0);
+  for (int idx = tid; idx < (2 * NG * Kc * 16) / 16; idx += BW_THREADS) reinterpret_cast<uint4*>(b_op)[idx] = make_uint4(0, 0, 0, 0);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const bool dbg = dbg_cta;
-      const uint32_t idesc64 = make_idesc_m(128, 2 * CN) | (1u << 16), idesc32 = make_idesc_m(128, CN) | (1u << 16);
+      const uint32_t idesc64 = make_idesc_m(128, 2 * BCN) | (1u << 16), idesc32 = make_idesc_m(128, N2) | (1u << 16);
       const uint32_t a_lbo = (uint32_t)AR * 16;
       const uint32_t bb = smem_u32(b_op), b_sbo = (uint32_t)Kc * 16;
       const int ksteps = Kc >> 4;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
           int row0 = 128 * m; if (row0 + 128 > AR) row0 = AR - 128;
           const uint64_t dah0 = make_desc(smem_u32(a_hi) + (uint32_t)row0 * 16, a_lbo, 128);
           const uint64_t dal0 = make_desc(smem_u32(a_lo) + (uint32_t)row0 * 16, a_lbo, 128);
-          const uint32_t d = tmem_base + (uint32_t)(m * 2 * CN);
+          const uint32_t d = tmem_base + (uint32_t)(m * 2 * BCN);
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t aoff = (uint64_t)(ks * ((2 * a_lbo) >> 4));
             const uint64_t db = make_desc(bb + (uint32_t)(ks * 16 * 16), 128, b_sbo);
@@ -587,13 +592,15 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
     // phase A (gate gradients): thread = (unit u of the slice, group of 8 clips); lanes run along the units, so the
     // dout / h_prev loads and the dgi / dgh stores are contiguous along j
     const int ga_u = tid % U, ga_cg = tid / U;
-    const bool ga_on = tid < 4 * U;
+    const bool ga_on = tid < NG * U;
     const int j = slice * U + ga_u;
     const bool j_ok = ga_on && j < H;
-    const int bA = tile * CN + ga_cg * 8;
+    const int bA = tile * BCN + ga_cg * 8;
     // phase B (reduce-scatter): thread = (row k of a 128-row tile, 16 clips)
     const int q = warp & 3, half = warp >> 2;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+    constexpr int G0 = (NG + 1) / 2;                     // clip groups of column half 0 (the rest go to half 1)
+    const int g_beg = half == 0 ? 0 : G0, g_end = half == 0 ? G0 : NG;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t rx_base = smem_u32(rx);
     float carry[8];
 #pragma unroll
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
         if (ga_on) {
 #pragma unroll 2
           for (int src = 0; src < S; ++src) {
-            const float4* sp = reinterpret_cast<const float4*>(rx + ((size_t)src * U + ga_u) * CN + ga_cg * 8);
+            const float4* sp = reinterpret_cast<const float4*>(rx + ((size_t)src * U + ga_u) * BCN + ga_cg * 8);
             const float4 a = sp[0], b4 = sp[1];
             carry[0] += a.x; carry[1] += a.y; carry[2] += a.z; carry[3] += a.w;
             carry[4] += b4.x; carry[5] += b4.y; carry[6] += b4.z; carry[7] += b4.w;
@@ -686,7 +693,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
             }
             const int c = g * U + ga_u;
             *reinterpret_cast<uint4*>(b_op + ((ga_cg * Kc) + c) * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(b_op + (((4 + ga_cg) * Kc) + c) * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(b_op + (((NG + ga_cg) * Kc) + c) * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
         fence_async_smem();
@@ -719,19 +726,29 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
         for (int m = 0; m < ntiles; ++m) {
           int row0 = 128 * m; if (row0 + 128 > AR) row0 = AR - 128;
           const int k = row0 + 32 * q + lane;
-          float v[16];
-          tmem_ld16_nowait(t_lane + (uint32_t)(m * 2 * CN), v);
-          if (p.x3) {
-            float w[16];
-            tmem_ld16_nowait(t_lane + (uint32_t)(m * 2 * CN + CN), w);
+          const bool send = k >= 128 * m && k < H;   // (rows below 128 m were delivered by the previous, overlapping tile)
+          const int d = k / U, ul = k - d * U;
+          const uint32_t dst = mapa(rx_base + (uint32_t)((((slice * U) + ul) * BCN) * 4), (uint32_t)(send ? d : slice));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
-          }
-          if (k >= 128 * m && k < S * U) {   // (rows below 128 m were delivered by the previous, overlapping tile)
-            const int d = k / U, ul = k - d * U;
-            const uint32_t dst = mapa(rx_base + (uint32_t)((((slice * U) + ul) * CN + half * 16) * 4), (uint32_t)d);
+          for (int gq = 0; gq < G0; ++gq) {
+            const int cgq = g_beg + gq;
+            if (cgq < g_end) {
+              float v[8];
+              tmem_ld8_nowait(t_lane + (uint32_t)(m * 2 * BCN + cgq * 8), v);
+              if (p.x3) {
+                float w[8];
+                tmem_ld8_nowait(t_lane + (uint32_t)(m * 2 * BCN + BCN + cgq * 8), w);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) st_cluster_v4(dst + (uint32_t)(i * 4), v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 8; ++i) v[i] += w[i];
+              } else {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              }
+              if (send) {
+                st_cluster_v4(dst + (uint32_t)(cgq * 32), v[0], v[1], v[2], v[3]);
+                st_cluster_v4(dst + (uint32_t)(cgq * 32 + 16), v[4], v[5], v[6], v[7]);
+              }
+            }
           }
         }
         tc_fence_before();
@@ -760,9 +777,11 @@ static inline size_t smem_bytes(int H) {
 }
 static inline size_t tile_bytes(int H) { return (size_t)2 * (128 + 2 * units_of(H)) * 33 * sizeof(float); }
 
-static inline size_t bwd_smem_bytes(int H) {
-  const int U = units_of(H), Kc = kc_of(U), Kpad = kpad_of(H), AR = Kpad < 128 ? 128 : Kpad;
-  return HDR + (size_t)2 * (Kc / 8) * AR * 16 + (size_t)8 * Kc * 16 + (size_t)slices_of(H) * U * CN * sizeof(float);
+static inline int bwd_rows(int H) { const int r = (H + 7) / 8 * 8; return r < 128 ? 128 : r; }
+static inline size_t bwd_smem_bytes(int H, int bcn) {
+  const int U = units_of(H), Kc = kc_of(U);
+  return HDR + (size_t)2 * (Kc / 8) * bwd_rows(H) * 16 + (size_t)2 * (bcn / 8) * Kc * 16 +
+         (size_t)slices_of(H) * U * bcn * sizeof(float);
 }
 
 }  // namespace gruc
@@ -821,52 +840,50 @@ extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward);
 namespace s2ag {
 // Clusters are gang-scheduled and independent, so more clusters than fit simply run in waves -- but a second wave
 // doubles the time of a latency-bound recurrence.  Measured on B200: 15 clusters of 8 CTAs (H = 300) are co-resident,
-// one short of the 16 that 256 clips x 2 directions need; 74 clusters of 2 CTAs (H = 64).  The cluster kernels are
-// therefore selected only when the whole launch is one wave (the L2-exchange kernels of umma_gru.cu otherwise).
-static bool one_wave(int H, int B, int backward) {
+// one short of the 16 that 256 clips x 2 directions need at 32 clips per cluster; 74 clusters of 2 CTAs (H = 64).  The
+// cluster kernels are therefore selected only when the whole launch is one wave (the L2-exchange kernels of
+// umma_gru.cu otherwise); the BPTT kernel also has a 40-clip instantiation (14 clusters for 256 clips).
+static int max_clusters(int H, int backward) {
   static int cache[2][512];
-  if (H >= 512) return false;
+  if (H >= 512) return 0;
   if (cache[backward][H] == 0) {
     const int n = s2ag_debug_gru_cluster_occupancy(H, backward);
     cache[backward][H] = n > 0 ? n : -1;
   }
-  return 2 * ((B + gruc::CN - 1) / gruc::CN) <= cache[backward][H];
+  return cache[backward][H];
 }
 bool gru_cluster_fwd_selected(int H, int B) {
   if (!gru_cluster_supported(H)) return false;
-  return (umma::g_dbg_flags & 2048) != 0 || one_wave(H, B, 0);
+  return (umma::g_dbg_flags & 2048) != 0 || 2 * ((B + gruc::CN - 1) / gruc::CN) <= max_clusters(H, 0);
 }
 bool gru_cluster_bwd_supported(int H) {
   if (umma::g_dbg_flags & 8192) return false;   // A/B switch: the L2-exchange BPTT kernel of umma_gru.cu
-  return H >= 8 && gruc::slices_of(H) <= gruc::MAXS && gruc::units_of(H) <= 40 && gruc::kpad_of(H) <= 384 &&
-         gruc::bwd_smem_bytes(H) <= 227 * 1024;
+  return H >= 8 && gruc::slices_of(H) <= gruc::MAXS && gruc::units_of(H) <= 40 && gruc::bwd_rows(H) <= 384 &&
+         gruc::bwd_smem_bytes(H, 32) <= 227 * 1024;
 }
-bool gru_cluster_bwd_selected(int H, int B) {
-  if (!gru_cluster_bwd_supported(H)) return false;
-  return (umma::g_dbg_flags & 2048) != 0 || one_wave(H, B, 1);
+// clips per cluster of the BPTT launch: 32, 40 when only that is one wave, 0 = use the L2-exchange kernel
+static int bwd_clips_per_cluster(int H, int B) {
+  if (!gru_cluster_bwd_supported(H)) return 0;
+  const int mc = max_clusters(H, 1);
+  if (2 * ((B + 31) / 32) <= mc) return 32;
+  if (gruc::bwd_smem_bytes(H, 40) <= 227 * 1024 && 2 * ((B + 39) / 40) <= mc) return 40;
+  return (umma::g_dbg_flags & 2048) != 0 ? 32 : 0;
 }
+bool gru_cluster_bwd_selected(int H, int B) { return bwd_clips_per_cluster(H, B) != 0; }
 
-int gru_cluster_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
-                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, int B, int T, int H, int x3,
-                    void* stream) {
+template <int BCN>
+static int launch_cluster_bwd(gruc::BwdParams p, void* stream) {
   using namespace gruc;
-  if (!gru_cluster_bwd_supported(H)) return S2AG_ERR_UNSUPPORTED;
-  auto kfn = &gru_cluster_bwd_kernel;
+  auto kfn = &gru_cluster_bwd_kernel<BCN>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return S2AG_ERR_LAUNCH;
     attr_set = true;
   }
-  BwdParams p;
-  p.dout = dout; p.lddout = lddout; p.dir_stride = dir_stride; p.out = out; p.gates = gates;
-  p.whh = whh_f; p.whh_dstride = whh_dstride; p.dgi = dgi; p.dgh = dgh;
-  p.B = B; p.T = T; p.H = H; p.S = slices_of(H); p.U = units_of(H); p.Kpad = kpad_of(H); p.Kc = kc_of(p.U); p.x3 = x3;
-  p.dbg = (umma::g_dbg_flags & 8) ? 1 : 0;
-  g_last_gru_kernel = 1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.S, (B + CN - 1) / CN, 2);
+  cfg.gridDim = dim3(p.S, (p.B + BCN - 1) / BCN, 2);
   cfg.blockDim = dim3(gruc::BW_THREADS);
-  cfg.dynamicSmemBytes = gruc::bwd_smem_bytes(H);
+  cfg.dynamicSmemBytes = gruc::bwd_smem_bytes(p.H, BCN);
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -875,6 +892,22 @@ int gru_cluster_bwd(const float* dout, long lddout, int dir_stride, const float*
   ++g_s2ag_launches;
   if (cudaLaunchKernelEx(&cfg, kfn, p) != cudaSuccess) return S2AG_ERR_LAUNCH;
   return S2AG_OK;
+}
+
+int gru_cluster_bwd(const float* dout, long lddout, int dir_stride, const float* out, const float* gates,
+                    const float* whh_f, long whh_dstride, float* dgi, float* dgh, int B, int T, int H, int x3,
+                    void* stream) {
+  using namespace gruc;
+  const int bcn = bwd_clips_per_cluster(H, B);
+  if (bcn == 0) return S2AG_ERR_UNSUPPORTED;
+  BwdParams p;
+  p.dout = dout; p.lddout = lddout; p.dir_stride = dir_stride; p.out = out; p.gates = gates;
+  p.whh = whh_f; p.whh_dstride = whh_dstride; p.dgi = dgi; p.dgh = dgh;
+  p.B = B; p.T = T; p.H = H; p.S = slices_of(H); p.U = units_of(H); p.Kpad = kpad_of(H); p.Kc = kc_of(p.U);
+  p.AR = bwd_rows(H); p.x3 = x3;
+  p.dbg = (umma::g_dbg_flags & 8) ? 1 : 0;
+  g_last_gru_kernel = 1;
+  return bcn == 40 ? launch_cluster_bwd<40>(p, stream) : launch_cluster_bwd<32>(p, stream);
 }
 }  // namespace s2ag
 
@@ -890,9 +923,9 @@ extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward) {
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = -1;
   if (backward) {
-    cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = bwd_smem_bytes(H);
-    cudaFuncSetAttribute(gru_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_bwd_kernel, &cfg) != cudaSuccess) return -1;
+    cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = bwd_smem_bytes(H, 32);
+    cudaFuncSetAttribute(gru_cluster_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_bwd_kernel<32>, &cfg) != cudaSuccess) return -1;
   } else {
     cfg.blockDim = dim3(s2ag::gruc::THREADS); cfg.dynamicSmemBytes = s2ag::gruc::smem_bytes(H);
     cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
