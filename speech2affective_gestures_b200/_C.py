@@ -72,6 +72,9 @@ def lib():
                 "libs2ag_b200.so is not built (%s). Run `python -m speech2affective_gestures_b200.build` "
                 "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path." % LIB_PATH)
         _lib = _bind(ctypes.CDLL(LIB_PATH))
+        if os.environ.get("S2AG_DEBUG_FLAGS") or os.environ.get("S2AG_DEBUG_FLAGS_FORCE"):
+            # bring-up / A-B switches of include/s2ag.h (s2ag_debug_flags); ..._FORCE bits survive later calls
+            _lib.s2ag_debug_flags(int(os.environ.get("S2AG_DEBUG_FLAGS", "0"), 0))
     return _lib
 
 
@@ -87,6 +90,8 @@ def is_emulated():
     return _emulated
 
 
+# S2AG_NVTX=1: one NVTX range per C-ABI call (named after the entry point) for nsys / ncu --nvtx timelines
+_NVTX = os.environ.get("S2AG_NVTX") == "1"
 _DEBUG_CAPTURE = os.environ.get("S2AG_DEBUG_CAPTURE") == "1"
 _dbg_state = {"bad": False}
 
@@ -100,7 +105,15 @@ def call(name, *args):
             _dbg_state["bad"] = True
             print("[s2ag debug] capture already INVALID (%d) before %s (thread %s)" % (
                 st, name, threading.current_thread().name), flush=True)
-    rc = getattr(l, name)(*args)
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(l, name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = getattr(l, name)(*args)
     if _DEBUG_CAPTURE and not _dbg_state["bad"]:
         st = l.s2ag_stream_capture_status(args[-1])
         if st not in (0, 1):

@@ -1,5 +1,6 @@
 // Library-level entry points: version, error string.
 #include "s2ag.h"
+#include <cstdlib>
 #include "common.cuh"
 #include <cstdarg>
 
@@ -71,7 +72,11 @@ extern "C" int s2ag_debug_read_timeline(long long* host, int n) {
 }
 extern "C" int s2ag_debug_flags(int flags) {
 #ifndef S2AG_EMU
-  s2ag::umma::g_dbg_flags = flags;
+  // S2AG_DEBUG_FLAGS_FORCE (environment): bits that stay set whatever the caller passes (sanitizer / A-B runs of
+  // test suites that set and reset flags themselves)
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("S2AG_DEBUG_FLAGS_FORCE"); forced = e ? (int)strtol(e, nullptr, 0) : 0; }
+  s2ag::umma::g_dbg_flags = flags | forced;
 #endif
   (void)flags;
   return S2AG_OK;

@@ -406,7 +406,8 @@ extern "C" int s2ag_attention_fwd(const float* x, const float* w1, const float* 
   S2AG_CHECK_ARG(x && w1 && b1 && w2 && b2 && out && N >= 0 && T > 0 && Hd > 0 && A > 0 && T <= 8192);
   if (N == 0) return S2AG_OK;
   auto kfn = &attention_fwd_kernel;
-  S2AG_LAUNCH(kfn, N, 256, T * sizeof(float), stream, x, w1, b1, w2, b2, out, alpha, T, Hd, A);
+  // (rounded up to 16 bytes: the compiler reads e[] with vector loads, compute-sanitizer memcheck flags the tail)
+  S2AG_LAUNCH(kfn, N, 256, ((T + 3) & ~3) * sizeof(float), stream, x, w1, b1, w2, b2, out, alpha, T, Hd, A);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }
@@ -418,7 +419,7 @@ extern "C" int s2ag_attention_bwd(const float* x, const float* w1, const float* 
   S2AG_CHECK_ARG(N >= 0 && T > 0 && Hd > 0 && A > 0 && A <= ATT_MAX_A && (2 * T + A * Hd + 2 * A) * 4 <= 48 * 1024);
   if (N == 0) return S2AG_OK;
   auto kfn = &attention_bwd_kernel;
-  S2AG_LAUNCH(kfn, N, 256, (2 * T + A * Hd + 2 * A) * sizeof(float), stream, x, w1, b1, w2, alpha, d_out, d_alpha, dx,
+  S2AG_LAUNCH(kfn, N, 256, ((2 * T + A * Hd + 2 * A + 3) & ~3) * sizeof(float), stream, x, w1, b1, w2, alpha, d_out, d_alpha, dx,
               dw1, db1, dw2, db2, T, Hd, A);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;

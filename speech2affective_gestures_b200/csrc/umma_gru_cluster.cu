@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_cluster_bwd_kernel(BwdParam
       if (step > 0) {
         mbar_wait_cluster(rx_full, (uint32_t)((step - 1) & 1));
         GRUB_MARK(2);
-        if (ga_on) {
+        if (j_ok) {   // (the slots of padding units j >= H are never written: their carry stays 0)
 #pragma unroll 2
           for (int src = 0; src < S; ++src) {
             const float4* sp = reinterpret_cast<const float4*>(rx + ((size_t)src * U + ga_u) * BCN + ga_cg * 8);

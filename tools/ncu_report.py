@@ -20,6 +20,14 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum ', 'dram__bytes_write.su
         'lts__t_sectors_op_read.sum ', 'lts__t_sectors_op_write.sum ', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum ', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum ']
 
 
+def I(x):
+    """ncu leaves cells empty for lines without samples and writes thousands separators in some locales"""
+    try:
+        return int(float(str(x).replace(',', '') or 0))
+    except ValueError:
+        return 0
+
+
 def page(rep, name):
     return subprocess.run(['ncu', '-i', rep, '--page', name, '--csv'], capture_output=True, text=True).stdout
 
@@ -35,18 +43,19 @@ def main(rep, nlines=25):
     h2 = src[1]
     isrc, ins, isamp = h2.index('Source'), h2.index('Instructions Executed'), h2.index('# Samples')
     data = src[2:]
-    tot = sum(int(r[ins]) for r in data)
-    tsamp = sum(int(r[isamp]) for r in data)
+    data = [r for r in data if len(r) > max(isrc, ins, isamp)]
+    tot = sum(I(r[ins]) for r in data)
+    tsamp = sum(I(r[isamp]) for r in data)
     op = collections.Counter()
     for r in data:
         m = re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[isrc])
-        op[m.group(2).split('.')[0] if m else '?'] += int(r[ins])
-    print('warp-instructions executed: %d ; opcode mix:' % tot, ', '.join('%s %.1f%%' % (k, 100 * v / tot) for k, v in op.most_common(14)))
+        op[m.group(2).split('.')[0] if m else '?'] += I(r[ins])
+    print('warp-instructions executed: %d ; opcode mix:' % tot, ', '.join('%s %.1f%%' % (k, 100 * v / max(tot, 1)) for k, v in op.most_common(14)))
     print('hottest SASS by stall samples (of %d):' % tsamp)
     stall_cols = [i for i, n in enumerate(h2) if n.startswith('stall_') and 'Not Issued' not in n]
-    for r in sorted(data, key=lambda r: -int(r[isamp]))[:nlines]:
-        st = sorted(((int(r[i]), h2[i]) for i in stall_cols if r[i] not in ('', '0')), reverse=True)[:2]
-        print('  %5.1f%%  exec %9s  %-70s %s' % (100 * int(r[isamp]) / max(tsamp, 1), r[ins], r[isrc].strip()[:70], st))
+    for r in sorted(data, key=lambda r: -I(r[isamp]))[:nlines]:
+        st = sorted(((I(r[i]), h2[i]) for i in stall_cols if r[i] not in ('', '0')), reverse=True)[:2]
+        print('  %5.1f%%  exec %9s  %-70s %s' % (100 * I(r[isamp]) / max(tsamp, 1), r[ins], r[isrc].strip()[:70], st))
 
 
 if __name__ == '__main__':
