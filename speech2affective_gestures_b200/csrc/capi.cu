@@ -81,6 +81,9 @@ extern "C" int s2ag_debug_flags(int flags) {
   (void)flags;
   return S2AG_OK;
 }
+#ifdef S2AG_EMU
+extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward) { (void)H; (void)backward; return S2AG_ERR_UNSUPPORTED; }
+#endif
 extern "C" unsigned long long s2ag_launch_count(void) { return g_s2ag_launches; }
 extern "C" int s2ag_stream_capture_status(void* stream) {
 #ifdef S2AG_EMU
