@@ -145,6 +145,20 @@ int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy, const int3
                 float* dx, long lddx, float* dgamma, float* dbeta, float* dadd, long lddadd,
                 double* ws, int groups, void* stream);
 
+/* ---- fused WavEncoder forward (net/multimodal_context_net_v2.py:14-33; frozen inside PoseGeneratorTriModal :277,
+ * called at :301) -- raw audio [B, L] -> features y[B, 34, 32] (row stride ldy floats), replacing the chain
+ * Conv1d(1,16,15,s5,p1600) BN LReLU Conv1d(16,32,15,s6) BN LReLU Conv1d(32,64,15,s6) BN LReLU Conv1d(64,32,15,s6).
+ * conv_w[4] / conv_b[4]: the four Conv1d weights [Cout][Cin][15] / biases; bn_*[3]: the three BatchNorm1d affine
+ * parameters (gamma / beta entries may be NULL) and running statistics.  These six arguments are HOST arrays of DEVICE
+ * pointers.  training != 0: batch statistics, running statistics updated with `momentum` (nn.BatchNorm1d train mode);
+ * 0: running statistics.  slope: LeakyReLU.  ws: caller-owned workspace of s2ag_wavencoder_ws_floats(B, L) floats,
+ * 32-byte aligned (raw conv2 / conv3 outputs + statistics; conv1's output is never stored).  4-5 launches (umma_wav.cu). */
+long s2ag_wavencoder_ws_floats(int B, int L);
+int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float* const* conv_w, const float* const* conv_b,
+                        const float* const* bn_gamma, const float* const* bn_beta, float* const* bn_rmean,
+                        float* const* bn_rvar, int training, float momentum, float eps, float slope, float* y, long ldy,
+                        float* ws, void* stream);
+
 /* ---- ST-GCN adjacency contraction (tgcn.py:67-69: einsum 'nkctv,kvw->nctw') -----------------
  * x[M, V, K*C] (channel index k*C + c), A[K,V,V], y[M, V, C]:  y[m,w,c] = sum_{k,v} x[m,v,k*C+c] A[k,v,w] */
 int s2ag_graph_fwd(const float* x, const float* A, float* y, int M, int V, int K, int C, void* stream);

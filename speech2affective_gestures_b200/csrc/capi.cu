@@ -83,6 +83,17 @@ extern "C" int s2ag_debug_flags(int flags) {
 }
 #ifdef S2AG_EMU
 extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward) { (void)H; (void)backward; return S2AG_ERR_UNSUPPORTED; }
+// umma_wav.cu (tcgen05) is not part of the emulation build: the host mirror uses the unfused chain there
+extern "C" long s2ag_wavencoder_ws_floats(int B, int L) { (void)B; (void)L; return 0; }
+extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float* const* conv_w, const float* const* conv_b,
+                                   const float* const* bn_gamma, const float* const* bn_beta, float* const* bn_rmean,
+                                   float* const* bn_rvar, int training, float momentum, float eps, float slope, float* y,
+                                   long ldy, float* ws, void* stream) {
+  (void)audio; (void)B; (void)L; (void)conv_w; (void)conv_b; (void)bn_gamma; (void)bn_beta; (void)bn_rmean; (void)bn_rvar;
+  (void)training; (void)momentum; (void)eps; (void)slope; (void)y; (void)ldy; (void)ws; (void)stream;
+  s2ag_set_error("s2ag_wavencoder_fwd: device build only");
+  return S2AG_ERR_UNSUPPORTED;
+}
 #endif
 extern "C" unsigned long long s2ag_launch_count(void) { return g_s2ag_launches; }
 extern "C" int s2ag_stream_capture_status(void* stream) {

@@ -16,10 +16,12 @@ B200-first design decisions (DESIGN.md has the detail):
     exposed as the usual nn.Parameters): one memset zeroes the gradients, one kernel runs Adam,
     one NCCL all-reduce averages them across ranks.
 """
+import os
+
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _C, ops
 from ..utils import ted_db_utils as ted_db
 from . import embedding_net as en
 from .tcn import TemporalConvNet
@@ -140,6 +142,11 @@ class WavEncoder(nn.Module):
 
     def forward(self, wav_data, out=None):
         f = self.feat_extractor
+        if not _C.is_emulated() and not (torch.is_grad_enabled() and any(q.requires_grad for q in f.parameters())) \
+                and os.environ.get("S2AG_WAV_FUSED", "1") != "0":
+            # frozen on the hot path (PoseGeneratorTriModal): conv1 recomputed per tile, BatchNorm + LeakyReLU applied while
+            # the next convolution stages its operand -- no normalised activation is ever written to HBM
+            return ops.wavencoder_fwd(wav_data, [f[0], f[3], f[6], f[9]], [f[1], f[4], f[7]], 0.3, out=out)
         x = wav_data.unsqueeze(-1)  # channels-last [B, L, 1]
         for ci in (0, 3, 6):
             x = ops.conv_bn_act(x, f[ci].weight, f[ci].bias, _conv1d_geom(f[ci]), bn=f[ci + 1], act=ops.ACT_LEAKY,

@@ -451,6 +451,44 @@ def conv_bn_act(x, conv_w, conv_b, geom, bn=None, act=ACT_NONE, slope=0.0, cmap=
                              None if out is None else Out(out))
 
 
+@torch.no_grad()
+def wavencoder_fwd(audio, convs, bns, slope, out=None):
+    """Fused WavEncoder forward (s2ag_wavencoder_fwd, csrc/umma_wav.cu): audio [B, L] -> [B, 34, 32] with the reference
+    layer geometry (net/multimodal_context_net_v2.py:17-28).  convs: the four nn.Conv1d, bns: the three nn.BatchNorm1d
+    parameter containers (train mode: batch statistics + running-statistic update; eval: running statistics).  No
+    autograd: the encoder is frozen on the hot path (PoseGeneratorTriModal)."""
+    _check(audio)
+    import ctypes as _ct
+    geom = [(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0]) for c in convs]
+    if geom != [(1, 16, 15, 5, 1600), (16, 32, 15, 6, 0), (32, 64, 15, 6, 0), (64, 32, 15, 6, 0)]:
+        raise _C.S2agError("wavencoder_fwd: layer geometry differs from the reference WavEncoder: %s" % (geom,))
+    training = bns[0].training
+    if any(b.training != training for b in bns) or _bn_groups[0] != 1:
+        raise _C.S2agError("wavencoder_fwd: mixed BatchNorm modes / statistic groups are not supported")
+    B, L = audio.shape
+    audio = audio.contiguous()
+    st = _stream(audio)
+    n_ws = _C.lib().s2ag_wavencoder_ws_floats(B, L)
+    if n_ws <= 0:
+        raise _C.S2agError("wavencoder_fwd: audio too short (%d samples)" % L)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=audio.device)
+    L1 = _conv_out(L, 15, 5, 1600, 1)
+    Lo = _conv_out(_conv_out(_conv_out(L1, 15, 6, 0, 1), 15, 6, 0, 1), 15, 6, 0, 1)
+    y = out if out is not None else _empty((B, Lo, 32), audio)
+    y2, ldy = _rows(y, 32)
+    arr = lambda ts: (_ct.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+    rep = _bn_repeat[0] if training else 1
+    mom = float(bns[0].momentum) if rep == 1 else 1.0 - (1.0 - float(bns[0].momentum)) ** rep
+    _C.call("s2ag_wavencoder_fwd", _p(audio), B, L, arr([c.weight for c in convs]), arr([c.bias for c in convs]),
+            arr([b.weight for b in bns]), arr([b.bias for b in bns]), arr([b.running_mean for b in bns]),
+            arr([b.running_var for b in bns]), 1 if training else 0, mom, float(bns[0].eps), float(slope), _p(y2), ldy,
+            _p(ws), st)
+    if training:
+        for b in bns:
+            b._s2ag_batches = getattr(b, "_s2ag_batches", 0) + rep
+    return y
+
+
 # ------------------------------------------------------------------------------------------ ST-GCN graph contraction
 class GraphFn(torch.autograd.Function):
     """y[n,t,w,c] = sum_{k,v} x[n,t,v,k*C+c] A[k,v,w]   (net/utils/tgcn.py:66-69)"""
