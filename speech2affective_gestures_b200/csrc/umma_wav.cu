@@ -6,9 +6,11 @@
 // What the unfused chain paid: conv1's [B,7891,16] fp32 output (129 MB at 256 clips) was written, re-read for the
 // statistics, re-read + rewritten by the normalisation, re-read by conv2 (and again for conv2 / conv3): ~18x the
 // algorithmic bytes (149 420 B per clip = audio in + features out).  Here:
-//   K1  wav_conv1_stats_kernel   audio -> per-channel shifted sums of conv1's output; the output itself is NEVER stored
-//   K2  wav_conv_kernel<16,32,1> audio -> conv1 recomputed per tile (fp32 SIMT) -> BN1 + LeakyReLU -> bf16 hi/lo operand
-//                                images in shared memory -> conv2 on tcgen05 -> raw conv2 output (L2-sized, 43 MB) + its sums
+//   K1  wav_prep_kernel          audio -> per-channel shifted sums of conv1's output (the output itself is NEVER stored;
+//                                audio spans arrive by double-buffered cp.async); extra blocks pack the weights of
+//                                conv2..4 once into bf16 hi/lo tensor-core operand images
+//   K2  wav_conv_kernel<16,32,1> audio -> conv1 recomputed per tile (fp32 SIMT) -> BN1 + LeakyReLU -> operand images in
+//                                shared memory -> conv2 on tcgen05 -> raw conv2 output (L2-sized, 43 MB) + its sums
 //   K3  wav_conv_kernel<32,64,0> raw conv2 -> BN2 + LeakyReLU while the operand is staged -> conv3 -> raw output + sums
 //   K4  wav_conv_kernel<64,32,0> raw conv3 -> BN3 + LeakyReLU while staged -> conv4 -> features (row stride ldy: the
 //                                GRU input buffer's column slice)
@@ -23,8 +25,16 @@
 // tap k is then one tcgen05.mma per 16 input channels whose A descriptor starts q rows into phase r.  Anchors run over
 // the concatenation of all clips with a per-clip pitch of ceil(Lin / 6) rows, so tiles cross clip boundaries without
 // padding waste (anchors o >= Lout of a clip are discarded).
+//
+// One persistent CTA per SM, warp-specialised, mbarrier pipeline over items = (tile, 16-channel pass):
+//   warps 0-7   producers: stage the operand images of item n into buffer n&1 (waits "empty": the MMAs of item n-2)
+//   warp  8     issuer: waits "full", issues the 15 taps x 3 (bf16x3) tcgen05.mma of the item into TMEM accumulator
+//               tile&1, commits "empty" and, after the tile's last pass, "tmem full"
+//   warps 9-16  epilogue: TMEM -> registers (bias, statistics) -> global, then "tmem empty"; overlaps the next tile
+// The whole weight tensor of the layer stays in shared memory (one TMA bulk copy of the pre-packed image per CTA).
 #include "s2ag.h"
 #include "gemm_umma.cuh"
+#include "gemm_umma_packed.cuh"
 
 namespace s2ag {
 namespace wav {
@@ -38,7 +48,11 @@ constexpr int S = 6;                   // stride of conv2..4 = number of phase i
 constexpr int QH = (KT - 1) / S;       // halo rows per phase image (2)
 constexpr int TM = 128;                // anchors per tile
 constexpr int R = TM + QH;             // staged rows per phase image
-constexpr int THREADS = 384, WORK = 256, NISS = 4, HDR = 1024;
+constexpr int RC = 132;                // chunk stride in rows (>= R, = 4 mod 8: conflict-free staging stores)
+constexpr int PST = 2 * RC + 1;        // phase stride in 16-byte units (= 1 mod 8)
+constexpr int A_PLANE = S * PST * 16;  // one bf16 plane of one operand buffer (16 channels)
+constexpr int A_BUF = 2 * A_PLANE;     // hi + lo
+constexpr int NPROD = 256, THREADS = 544, HDR = 1024;
 constexpr int AUD_FLOATS = 4096;       // audio span of one tile: <= 30 * R + 2 * 16 samples
 
 struct BnIn {                          // BatchNorm between the producing convolution and this one
@@ -52,11 +66,12 @@ struct Params {
   const float* x;                      // raw producer output [B, Lin, CIN] (FUSE1: the audio [B, L])
   int B, L, Lin, Lo, pitch;            // L: audio samples (FUSE1); Lin/Lo: input / output pixels per clip
   const float* w1; const float* b1;    // FUSE1: conv1 weight [16][1][15], bias
-  const float* w; const float* bias;   // this layer's weight [COUT][CIN][15], bias
+  const unsigned char* wpk;            // this layer's packed weight image [plane][tap][CIN/8][COUT][16 B]
+  const float* bias;
   float* y; long ldy;                  // raw (pre-BatchNorm) output rows, or the final features
   double* sums_out;                    // [2*COUT] or NULL
   BnIn bn;
-  int tiles; long total_rows;          // B * pitch
+  int tiles; int total_rows;           // B * pitch
   int x3;
 };
 
@@ -81,6 +96,13 @@ __device__ __forceinline__ void tmem_ld8w(uint32_t taddr, float (&r)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
+// 4-byte asynchronous copy global -> shared; !valid: zero fill (src is not read)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // BatchNorm scale / shift of channel c from the producer's shifted sums (training) or the running statistics
 __device__ __forceinline__ void bn_scale_shift(const BnIn& bn, int c, int C, bool update_running, float& scale, float& shift) {
@@ -105,34 +127,71 @@ __device__ __forceinline__ void bn_scale_shift(const BnIn& bn, int c, int C, boo
 }
 
 // ---------------------------------------------------------------------------------------------------------------- K1
-// sums[c] += sum_p (conv1(audio)[p, c] - b1[c]),  sums[16 + c] += sum_p (.)^2  over all pixels of all clips.
-// A block stages the audio span of 1024 consecutive output pixels of one clip (5130 samples) and every thread computes
-// 4 pixels x 16 channels (weights by 128-bit broadcast loads); the conv1 output never leaves registers.
+// blocks [0, stat_blocks): sums[c] += sum_p (conv1(audio)[p, c] - b1[c]), sums[16 + c] += sum_p (.)^2 over all pixels of
+// all clips.  A block takes items of 1024 consecutive output pixels of one clip; the item's audio span (5130 samples)
+// arrives by 4-byte cp.async into a double buffer while the previous item is computed; every thread computes 4 pixels x
+// 16 channels (weights by 128-bit broadcast loads).  The conv1 output never leaves registers.
+// blocks [stat_blocks, ...): pack the weights [COUT][CIN][15] of conv2..4 into the tensor-core operand images
+// [plane hi|lo][tap][CIN/8][COUT][16 B] that the consumer CTAs fetch with one TMA bulk copy.
 constexpr int K1_PIX = 1024, K1_SPAN = S1 * (K1_PIX - 1) + KT + 1;
-__global__ void __launch_bounds__(256) wav_conv1_stats_kernel(const float* __restrict__ audio, int B, int L, int L1,
-                                                              const float* __restrict__ w1, double* __restrict__ sums,
-                                                              int items_per_clip) {
+struct PackJob { const float* w; unsigned char* dst; int cin, cout; };
+struct PrepParams {
+  const float* audio; int B, L, L1; const float* w1; double* sums; int items_per_clip, stat_blocks;
+  PackJob job[3];
+};
+
+__global__ void __launch_bounds__(256) wav_prep_kernel(PrepParams p) {
   __shared__ __align__(16) float ws[KT][C1];
-  __shared__ float aud[K1_SPAN];
+  __shared__ float aud[2][K1_SPAN];
   __shared__ double red[2][C1];
   const int tid = threadIdx.x;
-  for (int i = tid; i < KT * C1; i += 256) ws[i / C1][i % C1] = __ldg(w1 + (i % C1) * KT + i / C1);
+  if ((int)blockIdx.x >= p.stat_blocks) {
+    const int nb = gridDim.x - p.stat_blocks, b = blockIdx.x - p.stat_blocks;
+    for (int l = 0; l < 3; ++l) {
+      const PackJob j = p.job[l];
+      const int kct = j.cin / 8, plane = KT * kct * j.cout * 16;
+      for (int idx = b * 256 + tid; idx < KT * kct * j.cout; idx += nb * 256) {
+        const int n = idx % j.cout; const int kc = (idx / j.cout) % kct; const int t = idx / (j.cout * kct);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(j.w + ((long)n * j.cin + kc * 8 + i) * KT + t);
+        uint4 hi, lo;
+        pack8w(v, hi, lo);
+        *reinterpret_cast<uint4*>(j.dst + (long)idx * 16) = hi;
+        *reinterpret_cast<uint4*>(j.dst + plane + (long)idx * 16) = lo;
+      }
+    }
+    return;
+  }
+  for (int i = tid; i < KT * C1; i += 256) ws[i / C1][i % C1] = __ldg(p.w1 + (i % C1) * KT + i / C1);
   if (tid < 2 * C1) red[tid / C1][tid % C1] = 0.0;
   float s1[C1], s2[C1];
 #pragma unroll
   for (int c = 0; c < C1; ++c) s1[c] = s2[c] = 0.f;
-  const int items = B * items_per_clip;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int clip = item / items_per_clip, p0 = (item - clip * items_per_clip) * K1_PIX;
-    const int npix = min(K1_PIX, L1 - p0);
+  const int items = p.B * p.items_per_clip;
+  auto prefetch = [&](int item, int buf) {
+    const int clip = item / p.items_per_clip, p0 = (item - clip * p.items_per_clip) * K1_PIX;
+    const int npix = min(K1_PIX, p.L1 - p0);
     const int s_lo = S1 * p0 - PAD1, span = S1 * (npix - 1) + KT;
-    const float* src = audio + (long)clip * L;
-    __syncthreads();
+    const float* src = p.audio + (long)clip * p.L;
+    const uint32_t dst = smem_u32(&aud[buf][0]);
     for (int i = tid; i < span; i += 256) {
       const int s = s_lo + i;
-      aud[i] = (s >= 0 && s < L) ? __ldg(src + s) : 0.f;
+      const bool ok = s >= 0 && s < p.L;
+      cp_async4(dst + 4u * i, src + (ok ? s : 0), ok);
     }
+  };
+  int item = blockIdx.x, buf = 0;
+  if (item < items) prefetch(item, 0);
+  cp_async_commit();
+  for (; item < items; item += p.stat_blocks, buf ^= 1) {
+    if (item + p.stat_blocks < items) prefetch(item + p.stat_blocks, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const int clip = item / p.items_per_clip, p0 = (item - clip * p.items_per_clip) * K1_PIX;
+    const int npix = min(K1_PIX, p.L1 - p0);
+    const float* a = aud[buf];
     float acc[4][C1];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -140,7 +199,7 @@ __global__ void __launch_bounds__(256) wav_conv1_stats_kernel(const float* __res
       for (int c = 0; c < C1; ++c) acc[i][c] = 0.f;
     int off[4]; bool ok[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const int p = tid + 256 * i; ok[i] = p < npix; off[i] = ok[i] ? S1 * p : 0; }
+    for (int i = 0; i < 4; ++i) { const int px = tid + 256 * i; ok[i] = px < npix; off[i] = ok[i] ? S1 * px : 0; }
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
       float wv[C1];
@@ -151,7 +210,7 @@ __global__ void __launch_bounds__(256) wav_conv1_stats_kernel(const float* __res
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float xv = aud[off[i] + t];
+        const float xv = a[off[i] + t];
 #pragma unroll
         for (int c = 0; c < C1; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
       }
@@ -162,36 +221,39 @@ __global__ void __launch_bounds__(256) wav_conv1_stats_kernel(const float* __res
 #pragma unroll
         for (int c = 0; c < C1; ++c) { s1[c] += acc[i][c]; s2[c] = fmaf(acc[i][c], acc[i][c], s2[c]); }
       }
+    __syncthreads();   // aud[buf] is overwritten by the prefetch of the next iteration
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int c = 0; c < C1; ++c) {
     const float a = s2ag_warp_sum(s1[c]), b = s2ag_warp_sum(s2[c]);
     if ((tid & 31) == 0) { atomicAdd(&red[0][c], (double)a); atomicAdd(&red[1][c], (double)b); }
   }
   __syncthreads();
-  if (tid < 2 * C1) atomicAdd(sums + tid, red[tid / C1][tid % C1]);
+  if (tid < 2 * C1) atomicAdd(p.sums + tid, red[tid / C1][tid % C1]);
 }
 
 // ------------------------------------------------------------------------------------------------------------ K2..K4
 template <int CIN, int COUT, bool FUSE1>
 struct Geo {
-  static constexpr int CPASS = CIN < 32 ? CIN : 32;      // input channels staged per pass
-  static constexpr int NPASS = CIN / CPASS;
-  static constexpr int KC = CPASS / 8;                   // 8-channel chunks per pass
-  static constexpr int PST = KC * R + 1;                 // phase stride in 16-byte units (+1: conflict-free staging)
-  static constexpr int A_PLANE = S * PST * 16;
-  static constexpr int W_PLANE = KT * KC * COUT * 16;
-  static constexpr int OFF_SC = HDR;                                  // scale[CIN], shift[CIN]
+  static constexpr int NPASS = CIN / 16;                 // 16 input channels per pipeline item
+  static constexpr int KCT = CIN / 8;                    // 8-channel chunks of the whole weight image
+  static constexpr int W_PLANE = KT * KCT * COUT * 16;
+  static constexpr int OFF_SC = HDR;                                  // scale[64], shift[64]
   static constexpr int OFF_W = OFF_SC + 2 * 64 * 4;
-  static constexpr int OFF_A = OFF_W + 2 * W_PLANE;
-  static constexpr int OFF_AUD = OFF_A + 2 * A_PLANE;                 // FUSE1: audio span + conv1 weights
-  static constexpr int OFF_W1 = OFF_AUD + (FUSE1 ? AUD_FLOATS * 4 : 0);
+  static constexpr int OFF_A = OFF_W + 2 * W_PLANE;                   // two operand buffers
+  static constexpr int OFF_AUD = OFF_A + 2 * A_BUF;                   // FUSE1: two audio spans + conv1 weights
+  static constexpr int OFF_W1 = OFF_AUD + (FUSE1 ? 2 * AUD_FLOATS * 4 : 0);
   static constexpr int OFF_RED = OFF_W1 + (FUSE1 ? (KT * C1 + C1) * 4 : 0);
   static constexpr int SMEM = OFF_RED + 2 * COUT * 8;
-  static constexpr uint32_t NCOLS = NISS * COUT <= 32 ? 32 : NISS * COUT <= 64 ? 64 : NISS * COUT <= 128 ? 128 : NISS * COUT <= 256 ? 256 : 512;
-  static_assert(CIN % CPASS == 0 && CPASS % 16 == 0 && COUT % 16 == 0 && NISS * COUT <= 512, "unsupported channel counts");
+  static constexpr uint32_t NCOLS = 2 * COUT <= 32 ? 32 : 2 * COUT <= 64 ? 64 : 2 * COUT <= 128 ? 128 : 256;
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128 && CIN <= 64, "unsupported channel counts");
   static_assert(!FUSE1 || CIN == C1, "the fused first layer produces 16 channels");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
+
+// header: mbarriers (8 bytes each) at these byte offsets
+constexpr int BAR_FULL = 0, BAR_EMPTY = 16, BAR_TFULL = 32, BAR_TEMPTY = 48, BAR_W = 64, TMEM_SLOT = 80;
 
 template <int CIN, int COUT, bool FUSE1>
 __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
@@ -200,23 +262,25 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t mma_bar = sbase;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 16);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TMEM_SLOT);
   float* sc = reinterpret_cast<float*>(smem + G::OFF_SC);
   float* sh = sc + 64;
-  unsigned char* w_hi = smem + G::OFF_W;
-  unsigned char* w_lo = w_hi + G::W_PLANE;
-  unsigned char* a_hi = smem + G::OFF_A;
-  unsigned char* a_lo = a_hi + G::A_PLANE;
+  unsigned char* a_base = smem + G::OFF_A;
   float* aud = reinterpret_cast<float*>(smem + G::OFF_AUD);
   float* w1s = reinterpret_cast<float*>(smem + G::OFF_W1);     // [KT][16] then bias[16]
   double* red = reinterpret_cast<double*>(smem + G::OFF_RED);  // [2][COUT]
 
   if (tid == 0) {
-    mbar_init(mma_bar, NISS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sbase + BAR_FULL + 8 * b, 8);     // one elected arrival per producer warp
+      mbar_init(sbase + BAR_EMPTY + 8 * b, 1);    // tcgen05.commit
+      mbar_init(sbase + BAR_TFULL + 8 * b, 1);    // tcgen05.commit
+      mbar_init(sbase + BAR_TEMPTY + 8 * b, 8);   // one elected arrival per epilogue warp
+    }
+    mbar_init(sbase + BAR_W, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(sbase + 16, G::NCOLS);
+  if (warp == 0) tmem_alloc(sbase + TMEM_SLOT, G::NCOLS);
   // ---- prologue: BatchNorm of the input as scale / shift (CTA 0 updates the running statistics once)
   if (tid < CIN) {
     float a, b;
@@ -228,74 +292,80 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
     for (int i = tid; i < KT * C1; i += THREADS) w1s[i] = __ldg(p.w1 + (i % C1) * KT + i / C1);
     if (tid < C1) w1s[KT * C1 + tid] = __ldg(p.b1 + tid);
   }
-  auto stage_w = [&](int pass) {
-    // element (tap t, out channel n, in channel pass*CPASS + kc*8 + i) of the reference weight [COUT][CIN][KT]
-    for (int idx = tid; idx < KT * G::KC * COUT; idx += THREADS) {
-      const int n = idx % COUT; const int kc = (idx / COUT) % G::KC; const int t = idx / (COUT * G::KC);
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(p.w + ((long)n * CIN + pass * G::CPASS + kc * 8 + i) * KT + t);
-      uint4 hi, lo;
-      pack8w(v, hi, lo);
-      *reinterpret_cast<uint4*>(w_hi + idx * 16) = hi;
-      *reinterpret_cast<uint4*>(w_lo + idx * 16) = lo;
-    }
-  };
-  if (G::NPASS == 1) stage_w(0);
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool vec_dst = (p.ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
-  constexpr int CH = COUT / 2;          // output channels per epilogue thread
-  float s1[CH], s2[CH];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) s1[c] = s2[c] = 0.f;
+  const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  uint32_t parity = 0;
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-    const long a0 = (long)tile * TM;
-    for (int pass = 0; pass < G::NPASS; ++pass, parity ^= 1u) {
-      if (G::NPASS > 1) stage_w(pass);
-      if (warp < 8) {
+  if (warp_u < 8) {
+    // =================================================================================================== producers
+    auto audio_prefetch = [&](int tile, int abuf) {
+      // audio span of the tile's rows: at most two clips (pitch > R); second clip's span starts at seg1
+      const int a0 = tile * TM;
+      const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
+      const int n0 = min(R, p.pitch - j0);
+      const uint32_t dst = smem_u32(aud + abuf * AUD_FLOATS);
+      const float* src0 = p.x + (long)c0 * p.L;
+      for (int i = tid; i < S1 * S * n0 + KT; i += NPROD) {
+        const int s = S1 * S * j0 - PAD1 + i;
+        const bool ok = s >= 0 && s < p.L;
+        cp_async4(dst + 4u * i, src0 + (ok ? s : 0), ok);
+      }
+      if (n0 < R) {
+        const int n1 = R - n0, seg1 = S1 * S * n0 + 16;
+        const bool clip_ok = c0 + 1 < p.B;
+        const float* src1 = p.x + (long)(clip_ok ? c0 + 1 : c0) * p.L;
+        for (int i = tid; i < S1 * S * n1 + KT; i += NPROD) {
+          const int s = i - PAD1;
+          const bool ok = clip_ok && s >= 0 && s < p.L;
+          cp_async4(dst + 4u * (seg1 + i), src1 + (ok ? s : 0), ok);
+        }
+      }
+    };
+    if (FUSE1) {
+      if (my_tiles > 0) audio_prefetch(blockIdx.x, 0);
+      cp_async_commit();
+    }
+    int n = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int a0 = tile * TM;
+      if (FUSE1) {
+        cp_async_wait<0>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // every producer's copies landed; conv1 of tile tl-1 is done
+        if (tl + 1 < my_tiles) audio_prefetch(tile + gridDim.x, (tl + 1) & 1);
+        cp_async_commit();
+      }
+      for (int pass = 0; pass < G::NPASS; ++pass, ++n) {
+        const int buf = n & 1;
+        if (n >= 2) mbar_wait(sbase + BAR_EMPTY + 8 * buf, ((n >> 1) - 1) & 1);
+        unsigned char* a_hi = a_base + buf * A_BUF;
+        unsigned char* a_lo = a_hi + A_PLANE;
         if (FUSE1) {
-          // ---- audio span of the tile's rows: at most two clips (pitch > R)
-          const int c0 = (int)(a0 / p.pitch), j0 = (int)(a0 - (long)c0 * p.pitch);
-          const int n0 = min(R, p.pitch - j0);           // rows of the first clip
-          const int seg1 = S1 * S * n0 + 16;             // smem offset of the second clip's span
-          for (int i = tid; i < S1 * S * n0 + KT; i += WORK) {
-            const int s = S1 * S * j0 - PAD1 + i;
-            aud[i] = (c0 < p.B && s >= 0 && s < p.L) ? __ldg(p.x + (long)c0 * p.L + s) : 0.f;
-          }
-          if (n0 < R) {
-            const int n1 = R - n0;
-            for (int i = tid; i < S1 * S * n1 + KT; i += WORK) {
-              const int s = i - PAD1;
-              aud[seg1 + i] = (c0 + 1 < p.B && s >= 0 && s < p.L) ? __ldg(p.x + (long)(c0 + 1) * p.L + s) : 0.f;
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          // ---- conv1 (fp32 SIMT) + BN1 + LeakyReLU -> operand images; thread = 3 pixels x 16 channels
-          for (int base = 0; base < R * S; base += 3 * WORK) {
+          // ---- conv1 (fp32 SIMT) + BN1 + LeakyReLU -> operand images; thread = 2 pixels x 16 channels at a time
+          const float* au = aud + (tl & 1) * AUD_FLOATS;
+          const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
+          const int n0 = min(R, p.pitch - j0);
+          const int seg1 = S1 * S * n0 + 16;
+          for (int base = 0; base < R * S; base += 2 * NPROD) {
             if (base + tid >= R * S) break;
-            int off[3], dst[3]; bool ok[3], real[3];
+            int off[2], dst[2]; bool ok[2], real[2];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const int idx = base + tid + WORK * i;       // idx = r * R + row: consecutive threads, consecutive rows
+            for (int i = 0; i < 2; ++i) {
+              const int idx = base + tid + NPROD * i;      // idx = r * R + row: consecutive threads, consecutive rows
               ok[i] = idx < R * S;
               const int r = ok[i] ? idx / R : 0, row = ok[i] ? idx - r * R : 0;
               const bool second = row >= n0;
               const int j = second ? row - n0 : j0 + row;
               const int pix = S * j + r;
               real[i] = ok[i] && (c0 + (second ? 1 : 0)) < p.B && pix < p.Lin;
-              off[i] = (second ? seg1 + S1 * pix : S1 * (pix - S * j0));
-              if (!real[i]) off[i] = 0;
-              dst[i] = (r * G::PST + row) * 16;
+              off[i] = real[i] ? (second ? seg1 + S1 * pix : S1 * (pix - S * j0)) : 0;
+              dst[i] = (r * PST + row) * 16;
             }
-            float acc[3][C1];
+            float acc[2][C1];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
               for (int c = 0; c < C1; ++c) acc[i][c] = 0.f;
 #pragma unroll
@@ -307,14 +377,14 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
                 wv[4 * c4] = q.x; wv[4 * c4 + 1] = q.y; wv[4 * c4 + 2] = q.z; wv[4 * c4 + 3] = q.w;
               }
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const float xv = aud[off[i] + t];
+              for (int i = 0; i < 2; ++i) {
+                const float xv = au[off[i] + t];
 #pragma unroll
                 for (int c = 0; c < C1; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
               }
             }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < 2; ++i) {
               if (!ok[i]) continue;
 #pragma unroll
               for (int kc = 0; kc < 2; ++kc) {
@@ -327,129 +397,162 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
                 }
                 uint4 hi, lo;
                 pack8w(v, hi, lo);
-                *reinterpret_cast<uint4*>(a_hi + dst[i] + kc * R * 16) = hi;
-                if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i] + kc * R * 16) = lo;
+                *reinterpret_cast<uint4*>(a_hi + dst[i] + kc * RC * 16) = hi;
+                if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i] + kc * RC * 16) = lo;
               }
             }
           }
         } else {
-          // ---- raw producer output -> BN + LeakyReLU -> operand images; item = (local pixel, 8-channel chunk),
-          //      consecutive threads read consecutive 32-byte segments
-          for (int it = tid; it < R * S * G::KC; it += WORK) {
-            const int kc = it % G::KC, lp = it / G::KC;
-            const int row = lp / S, r = lp - row * S;
-            const long g = a0 + row;
-            const int c = (int)(g / p.pitch), j = (int)(g - (long)c * p.pitch);
-            const int pix = S * j + r;
-            float v[8];
-            if (c < p.B && pix < p.Lin) {
-              const int ch = pass * G::CPASS + kc * 8;
-              const float4* src = reinterpret_cast<const float4*>(p.x + ((long)c * p.Lin + pix) * CIN + ch);
-              const float4 a = __ldg(src), b = __ldg(src + 1);
-              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          // ---- raw producer output -> BN + LeakyReLU -> operand images; item = (local pixel, 8-channel chunk):
+          //      consecutive threads read consecutive 32-byte segments; 4 items (8 x LDG.128) in flight per thread
+          const int ch0 = pass * 16;
+          constexpr int ITEMS = R * S * 2;
+          for (int base = 0; base < ITEMS; base += 4 * NPROD) {
+            float4 va[4], vb[4]; int dst[4]; bool ok[4], real[4]; int chv[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float tv = fmaf(v[e], sc[ch + e], sh[ch + e]);
-                v[e] = tv > 0.f ? tv : tv * p.bn.slope;
+            for (int i = 0; i < 4; ++i) {
+              const int it = base + tid + NPROD * i;
+              ok[i] = it < ITEMS;
+              const int kc = it & 1, lp = it >> 1;
+              const int row = lp / S, r = lp - row * S;
+              const int g = a0 + row;
+              const int c = g / p.pitch, j = g - c * p.pitch;
+              const int pix = S * j + r;
+              real[i] = ok[i] && c < p.B && pix < p.Lin;
+              chv[i] = ch0 + kc * 8;
+              dst[i] = (r * PST + kc * RC + row) * 16;
+              if (real[i]) {
+                const float4* src = reinterpret_cast<const float4*>(p.x + ((long)c * p.Lin + pix) * CIN + chv[i]);
+                va[i] = __ldg(src); vb[i] = __ldg(src + 1);
+              } else {
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f); vb[i] = va[i];
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.f;
             }
-            uint4 hi, lo;
-            pack8w(v, hi, lo);
-            const int dst = (r * G::PST + kc * R + row) * 16;
-            *reinterpret_cast<uint4*>(a_hi + dst) = hi;
-            if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst) = lo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!ok[i]) continue;
+              float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+              if (real[i]) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float tv = fmaf(v[e], sc[chv[i] + e], sh[chv[i] + e]);
+                  v[e] = tv > 0.f ? tv : tv * p.bn.slope;
+                }
+              }
+              uint4 hi, lo;
+              pack8w(v, hi, lo);
+              *reinterpret_cast<uint4*>(a_hi + dst[i]) = hi;
+              if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i]) = lo;
+            }
           }
         }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(sbase + BAR_FULL + 8 * buf);
       }
-      fence_async_smem();
-      __syncthreads();
-      if (warp_u >= 8 && elect_one()) {
-        // ---- issuer `iss`: taps iss, iss + NISS, ... of this pass into accumulator iss
-        const int iss = warp_u - 8;
-        tc_fence_after();
-        const uint32_t idesc = make_idesc(COUT);
-        const uint32_t sa = smem_u32(a_hi), sw = smem_u32(w_hi);
-        const uint32_t d = tmem_base + (uint32_t)(iss * COUT);
-        uint32_t cnt = pass;   // pass > 0 accumulates onto pass 0
-        for (int t = iss; t < KT; t += NISS) {
-          const int q = t / S, r = t - q * S;
-#pragma unroll
-          for (int k2 = 0; k2 < G::KC / 2; ++k2) {
-            const uint32_t ah = sa + (uint32_t)((r * G::PST + 2 * k2 * R + q) * 16), al = ah + (uint32_t)G::A_PLANE;
-            const uint32_t wh = sw + (uint32_t)(((t * G::KC + 2 * k2) * COUT) * 16), wl = wh + (uint32_t)G::W_PLANE;
-            const uint64_t dah = make_desc(ah, R * 16, 128), dwh = make_desc(wh, COUT * 16, 128);
+    }
+    if (FUSE1) cp_async_wait<0>();
+  } else if (warp_u == 8) {
+    // ====================================================================================================== issuer
+    if (elect_one()) {
+      // the layer's whole weight image: one expect_tx, bulk copies of <= 32 KB
+      constexpr uint32_t WB = 2u * G::W_PLANE;
+      mbar_expect_tx(sbase + BAR_W, WB);
+      for (uint32_t o = 0; o < WB; o += 32768u)
+        bulk_g2s(sbase + G::OFF_W + o, p.wpk + o, WB - o < 32768u ? WB - o : 32768u, sbase + BAR_W);
+      mbar_wait(sbase + BAR_W, 0);
+      const uint32_t idesc = make_idesc(COUT);
+      const uint32_t sw = sbase + G::OFF_W;
+      int n = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int acc = tl & 1;
+        const uint32_t d = tmem_base + (uint32_t)(acc * COUT);
+        if (tl >= 2) mbar_wait(sbase + BAR_TEMPTY + 8 * acc, ((tl >> 1) - 1) & 1);
+        for (int pass = 0; pass < G::NPASS; ++pass, ++n) {
+          const int buf = n & 1;
+          mbar_wait(sbase + BAR_FULL + 8 * buf, (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sa = sbase + G::OFF_A + buf * A_BUF;
+          uint32_t cnt = pass;
+#pragma unroll 1
+          for (int t = 0; t < KT; ++t) {
+            const int q = t / S, r = t - q * S;
+            const uint32_t ah = sa + (uint32_t)((r * PST + q) * 16), al = ah + (uint32_t)A_PLANE;
+            const uint32_t wh = sw + (uint32_t)(((t * G::KCT + 2 * pass) * COUT) * 16), wl = wh + (uint32_t)G::W_PLANE;
+            const uint64_t dah = make_desc(ah, RC * 16, 128), dwh = make_desc(wh, COUT * 16, 128);
             if (p.x3) {
-              mma_bf16(d, make_desc(al, R * 16, 128), dwh, idesc, cnt ? 1u : 0u); ++cnt;
+              mma_bf16(d, make_desc(al, RC * 16, 128), dwh, idesc, cnt ? 1u : 0u); ++cnt;
               mma_bf16(d, dah, make_desc(wl, COUT * 16, 128), idesc, 1u); ++cnt;
             }
             mma_bf16(d, dah, dwh, idesc, cnt ? 1u : 0u); ++cnt;
           }
+          mma_commit(sbase + BAR_EMPTY + 8 * buf);
         }
-        mma_commit(mma_bar);
+        mma_commit(sbase + BAR_TFULL + 8 * acc);
       }
-      mbar_wait(mma_bar, parity);
-      tc_fence_after();
-      if (pass + 1 < G::NPASS) { tc_fence_before(); __syncthreads(); }   // operands of the next pass overwrite these
     }
-    if (warp < 8) {
-      // ---- epilogue: thread = anchor, warpgroup = half of the output channels
-      const int row = (warp & 3) * 32 + lane;
-      const long a = a0 + row;
-      const int c = (int)(a / p.pitch), o = (int)(a - (long)c * p.pitch);
+  } else {
+    // ==================================================================================================== epilogue
+    // warps 9..16: TMEM lane quadrant = warp & 3, channel half = (warp - 9) >> 2
+    constexpr int CH = COUT / 2;
+    float s1[CH], s2[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s1[c] = s2[c] = 0.f;
+    const int quad = warp & 3, half = (warp - 9) >> 2;
+    const int c_beg = half * CH;
+    const bool vec_dst = (p.ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int acc = tl & 1;
+      mbar_wait(sbase + BAR_TFULL + 8 * acc, (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * COUT + c_beg);
+      const int a = tile * TM + quad * 32 + lane;
+      const int c = a / p.pitch, o = a - c * p.pitch;
       const bool ok = c < p.B && o < p.Lo;
-      float* dst = p.y + ((long)c * p.Lo + o) * p.ldy;
-      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      const int c_beg = (warp >> 2) * CH;
+      float* dst = p.y + ((long)c * p.Lo + o) * p.ldy + c_beg;
 #pragma unroll
       for (int cg = 0; cg < CH / 8; ++cg) {
-        const int c0 = c_beg + cg * 8;
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int ai = 0; ai < NISS; ++ai) {
-          float v[8];
-          tmem_ld8w(t_lane + (uint32_t)(ai * COUT + c0), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        float t8[8];
+        tmem_ld8w(t_addr + cg * 8, t8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cg == CH / 8 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(sbase + BAR_TEMPTY + 8 * acc);   // the accumulator may be overwritten
         }
         if (ok) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { s1[cg * 8 + i] += acc[i]; s2[cg * 8 + i] = fmaf(acc[i], acc[i], s2[cg * 8 + i]); }
           float val[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) val[i] = acc[i] + __ldg(p.bias + c0 + i);
+          for (int i = 0; i < 8; ++i) {
+            const float d = t8[i];
+            s1[cg * 8 + i] += d; s2[cg * 8 + i] = fmaf(d, d, s2[cg * 8 + i]);
+            val[i] = d + __ldg(p.bias + c_beg + cg * 8 + i);
+          }
           if (vec_dst) {
             asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(val[0]), "f"(val[1]), "f"(val[2]),
-                         "f"(val[3]), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]), "l"(dst + c0)
+                         "f"(val[3]), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]), "l"(dst + cg * 8)
                          : "memory");
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[c0 + i] = val[i];
+            for (int i = 0; i < 8; ++i) dst[cg * 8 + i] = val[i];
           }
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();
-  }
-  // ---- per-channel sums of this layer's raw output (relative to its bias) for the next BatchNorm
-  if (p.sums_out) {
-    if (warp < 8) {
-      const int c_beg = (warp >> 2) * CH;
+    // per-channel sums of this layer's raw output (relative to its bias) for the next BatchNorm
+    if (p.sums_out) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const float a = s2ag_warp_sum(s1[c]), b = s2ag_warp_sum(s2[c]);
         if (lane == 0) { atomicAdd(&red[c_beg + c], (double)a); atomicAdd(&red[COUT + c_beg + c], (double)b); }
       }
     }
-    __syncthreads();
-    for (int i = tid; i < 2 * COUT; i += THREADS) atomicAdd(p.sums_out + i, red[i]);
   }
+  tc_fence_before();
+  __syncthreads();
+  if (p.sums_out)
+    for (int i = tid; i < 2 * COUT; i += THREADS) atomicAdd(p.sums_out + i, red[i]);
   if (warp == 0) tmem_dealloc(tmem_base, G::NCOLS);
 }
 
@@ -464,13 +567,15 @@ static int launch_layer(Params& p, int sms, void* stream) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM) != cudaSuccess) return -1;
     attr_set = true;
   }
-  p.total_rows = (long)p.B * p.pitch;
-  p.tiles = (int)((p.total_rows + TM - 1) / TM);
+  p.total_rows = p.B * p.pitch;
+  p.tiles = (p.total_rows + TM - 1) / TM;
   p.x3 = umma::g_precision == 0 ? 1 : 0;
   int grid = sms < p.tiles ? sms : p.tiles;
   S2AG_LAUNCH(kfn, grid, THREADS, G::SMEM, stream, p);
   return 0;
 }
+
+constexpr long WPK2 = 2L * KT * 2 * 32 * 16, WPK3 = 2L * KT * 4 * 64 * 16, WPK4 = 2L * KT * 8 * 32 * 16;
 
 }  // namespace wav
 }  // namespace s2ag
@@ -484,7 +589,8 @@ extern "C" long s2ag_wavencoder_ws_floats(int B, int L) {
   const int L2 = conv_len(L1, KT, S, 0);
   if (L2 < KT) return 0;
   const int L3 = conv_len(L2, KT, S, 0);
-  return (long)B * ((long)L2 * 32 + (long)L3 * 64) + 2 * (2 * 16 + 2 * 32 + 2 * 64) + 64;
+  if (L3 < KT) return 0;
+  return (long)B * ((long)L2 * 32 + (long)L3 * 64) + 2 * (2 * 16 + 2 * 32 + 2 * 64) + (WPK2 + WPK3 + WPK4) / 4 + 64;
 }
 
 extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float* const* conv_w,
@@ -502,7 +608,7 @@ extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float
   const int L3 = conv_len(L2, KT, S, 0);
   S2AG_CHECK_ARG(L3 >= KT);
   const int L4 = conv_len(L3, KT, S, 0);
-  S2AG_CHECK_ARG(ldy >= 32 && (long)B * L1 < (1L << 31));
+  S2AG_CHECK_ARG(ldy >= 32 && (long)B * L1 < (1L << 31) && (long)B * L < (1L << 40));
   S2AG_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 31) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   static int sms = 0;
@@ -510,18 +616,26 @@ extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float
     int dev = 0; cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  // workspace: raw conv2 output, raw conv3 output, sums (doubles) of conv1 / conv2 / conv3
+  // workspace: raw conv2 output, raw conv3 output, sums (doubles) of conv1 / conv2 / conv3, packed weight images
   float* y2 = ws;
   float* y3 = y2 + (long)B * L2 * 32;
-  double* sums = reinterpret_cast<double*>(y3 + (long)B * L3 * 64 + (((long)B * L3 * 64) & 1));
-  S2AG_CHECK_ARG((reinterpret_cast<uintptr_t>(sums) & 7) == 0);
+  double* sums = reinterpret_cast<double*>(y3 + (long)B * L3 * 64);
   double* sums1 = sums; double* sums2 = sums + 2 * 16; double* sums3 = sums2 + 2 * 32;
-  if (training) {
-    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (16 + 32 + 64), st);
-    const int ipc = (L1 + K1_PIX - 1) / K1_PIX;
-    int grid = B * ipc; if (grid > sms * 4) grid = sms * 4;
-    auto k1 = &wav_conv1_stats_kernel;
-    S2AG_LAUNCH(k1, grid, 256, 0, stream, audio, B, L, L1, conv_w[0], sums1, ipc);
+  unsigned char* wpk2 = reinterpret_cast<unsigned char*>(sums + 2 * (16 + 32 + 64));
+  unsigned char* wpk3 = wpk2 + WPK2;
+  unsigned char* wpk4 = wpk3 + WPK3;
+  S2AG_CHECK_ARG((reinterpret_cast<uintptr_t>(wpk2) & 15) == 0);
+  {
+    if (training) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (16 + 32 + 64), st);
+    PrepParams pp;
+    pp.audio = audio; pp.B = B; pp.L = L; pp.L1 = L1; pp.w1 = conv_w[0]; pp.sums = sums1;
+    pp.items_per_clip = (L1 + K1_PIX - 1) / K1_PIX;
+    int sb = training ? B * pp.items_per_clip : 0;
+    if (sb > 2 * sms) sb = 2 * sms;
+    pp.stat_blocks = sb;
+    pp.job[0] = {conv_w[1], wpk2, 16, 32}; pp.job[1] = {conv_w[2], wpk3, 32, 64}; pp.job[2] = {conv_w[3], wpk4, 64, 32};
+    auto k1 = &wav_prep_kernel;
+    S2AG_LAUNCH(k1, sb + 8, 256, 0, stream, pp);
   }
   auto bn_in = [&](int i, double* s, long count) {
     BnIn b;
@@ -532,17 +646,17 @@ extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float
   Params p;
   // conv1 (recomputed) + BN1 -> conv2
   p.x = audio; p.B = B; p.L = L; p.Lin = L1; p.Lo = L2; p.pitch = (L1 + S - 1) / S;
-  p.w1 = conv_w[0]; p.b1 = conv_b[0]; p.w = conv_w[1]; p.bias = conv_b[1]; p.y = y2; p.ldy = 32;
+  p.w1 = conv_w[0]; p.b1 = conv_b[0]; p.wpk = wpk2; p.bias = conv_b[1]; p.y = y2; p.ldy = 32;
   p.sums_out = training ? sums2 : nullptr; p.bn = bn_in(0, sums1, (long)B * L1);
   S2AG_CHECK_ARG(p.pitch > R);
   if (launch_layer<16, 32, true>(p, sms, stream)) { s2ag_set_error("wavencoder: shared memory attribute"); return S2AG_ERR_LAUNCH; }
   // BN2 -> conv3
   p.x = y2; p.Lin = L2; p.Lo = L3; p.pitch = (L2 + S - 1) / S; p.w1 = nullptr; p.b1 = nullptr;
-  p.w = conv_w[2]; p.bias = conv_b[2]; p.y = y3; p.ldy = 64; p.sums_out = training ? sums3 : nullptr;
+  p.wpk = wpk3; p.bias = conv_b[2]; p.y = y3; p.ldy = 64; p.sums_out = training ? sums3 : nullptr;
   p.bn = bn_in(1, sums2, (long)B * L2);
   if (launch_layer<32, 64, false>(p, sms, stream)) { s2ag_set_error("wavencoder: shared memory attribute"); return S2AG_ERR_LAUNCH; }
   // BN3 -> conv4 -> features
-  p.x = y3; p.Lin = L3; p.Lo = L4; p.pitch = (L3 + S - 1) / S; p.w = conv_w[3]; p.bias = conv_b[3]; p.y = y; p.ldy = ldy;
+  p.x = y3; p.Lin = L3; p.Lo = L4; p.pitch = (L3 + S - 1) / S; p.wpk = wpk4; p.bias = conv_b[3]; p.y = y; p.ldy = ldy;
   p.sums_out = nullptr; p.bn = bn_in(2, sums3, (long)B * L3);
   if (launch_layer<64, 32, false>(p, sms, stream)) { s2ag_set_error("wavencoder: shared memory attribute"); return S2AG_ERR_LAUNCH; }
   S2AG_CHECK_LAUNCH();
