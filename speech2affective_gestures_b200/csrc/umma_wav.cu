@@ -27,10 +27,11 @@
 // padding waste (anchors o >= Lout of a clip are discarded).
 //
 // One persistent CTA per SM, warp-specialised, mbarrier pipeline over items = (tile, 16-channel pass):
-//   warps 0-7   producers: stage the operand images of item n into buffer n&1 (waits "empty": the MMAs of item n-2)
-//   warp  8     issuer: waits "full", issues the 15 taps x 3 (bf16x3) tcgen05.mma of the item into TMEM accumulator
+//   warps 0-13  producers: stage the operand images of item n into buffer n&1 (waits "empty": the MMAs of item n-2);
+//               K3/K4: two groups of 7 warps alternate items so one group's loads fly while the other converts
+//   warp  14    issuer: waits "full", issues the 15 taps x 3 (bf16x3) tcgen05.mma of the item into TMEM accumulator
 //               tile&1, commits "empty" and, after the tile's last pass, "tmem full"
-//   warps 9-16  epilogue: TMEM -> registers (bias, statistics) -> global, then "tmem empty"; overlaps the next tile
+//   warps 15-22 epilogue: TMEM -> registers (bias, statistics) -> global, then "tmem empty"; overlaps the next tile
 // The whole weight tensor of the layer stays in shared memory (one TMA bulk copy of the pre-packed image per CTA).
 #include "s2ag.h"
 #include "gemm_umma.cuh"
@@ -52,7 +53,8 @@ constexpr int RC = 132;                // chunk stride in rows (>= R, = 4 mod 8:
 constexpr int PST = 2 * RC + 1;        // phase stride in 16-byte units (= 1 mod 8)
 constexpr int A_PLANE = S * PST * 16;  // one bf16 plane of one operand buffer (16 channels)
 constexpr int A_BUF = 2 * A_PLANE;     // hi + lo
-constexpr int NPROD = 256, THREADS = 544, HDR = 1024;
+constexpr int NPW = 14;               // staging warps (the fused first layer: one group; the others: two groups of 7)
+constexpr int NPROD = NPW * 32, THREADS = (NPW + 1 + 8) * 32, HDR = 1024;
 constexpr int AUD_FLOATS = 4096;       // audio span of one tile: <= 30 * R + 2 * 16 samples
 
 struct BnIn {                          // BatchNorm between the producing convolution and this one
@@ -192,34 +194,38 @@ __global__ void __launch_bounds__(256) wav_prep_kernel(PrepParams p) {
     const int clip = item / p.items_per_clip, p0 = (item - clip * p.items_per_clip) * K1_PIX;
     const int npix = min(K1_PIX, p.L1 - p0);
     const float* a = aud[buf];
-    float acc[4][C1];
+    float2 acc[4][C1 / 2];   // packed fp32 pairs: FFMA2 (two FMAs per issue slot)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < C1; ++c) acc[i][c] = 0.f;
+      for (int c = 0; c < C1 / 2; ++c) acc[i][c] = make_float2(0.f, 0.f);
     int off[4]; bool ok[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const int px = tid + 256 * i; ok[i] = px < npix; off[i] = ok[i] ? S1 * px : 0; }
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
-      float wv[C1];
+      float2 wv[C1 / 2];
 #pragma unroll
       for (int c4 = 0; c4 < C1 / 4; ++c4) {
         const float4 q = *reinterpret_cast<const float4*>(&ws[t][4 * c4]);
-        wv[4 * c4] = q.x; wv[4 * c4 + 1] = q.y; wv[4 * c4 + 2] = q.z; wv[4 * c4 + 3] = q.w;
+        wv[2 * c4] = make_float2(q.x, q.y); wv[2 * c4 + 1] = make_float2(q.z, q.w);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float xv = a[off[i] + t];
+        const float2 x2 = make_float2(xv, xv);
 #pragma unroll
-        for (int c = 0; c < C1; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
+        for (int c = 0; c < C1 / 2; ++c) acc[i][c] = __ffma2_rn(x2, wv[c], acc[i][c]);
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) {
 #pragma unroll
-        for (int c = 0; c < C1; ++c) { s1[c] += acc[i][c]; s2[c] = fmaf(acc[i][c], acc[i][c], s2[c]); }
+        for (int c = 0; c < C1 / 2; ++c) {
+          s1[2 * c] += acc[i][c].x; s2[2 * c] = fmaf(acc[i][c].x, acc[i][c].x, s2[2 * c]);
+          s1[2 * c + 1] += acc[i][c].y; s2[2 * c + 1] = fmaf(acc[i][c].y, acc[i][c].y, s2[2 * c + 1]);
+        }
       }
     __syncthreads();   // aud[buf] is overwritten by the prefetch of the next iteration
   }
@@ -244,7 +250,7 @@ struct Geo {
   static constexpr int OFF_A = OFF_W + 2 * W_PLANE;                   // two operand buffers
   static constexpr int OFF_AUD = OFF_A + 2 * A_BUF;                   // FUSE1: two audio spans + conv1 weights
   static constexpr int OFF_W1 = OFF_AUD + (FUSE1 ? 2 * AUD_FLOATS * 4 : 0);
-  static constexpr int OFF_RED = OFF_W1 + (FUSE1 ? (KT * C1 + C1) * 4 : 0);
+  static constexpr int OFF_RED = OFF_W1 + (FUSE1 ? KT * C1 * 4 : 0);
   static constexpr int SMEM = OFF_RED + 2 * COUT * 8;
   static constexpr uint32_t NCOLS = 2 * COUT <= 32 ? 32 : 2 * COUT <= 64 ? 64 : 2 * COUT <= 128 ? 128 : 256;
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128 && CIN <= 64, "unsupported channel counts");
@@ -267,12 +273,12 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
   float* sh = sc + 64;
   unsigned char* a_base = smem + G::OFF_A;
   float* aud = reinterpret_cast<float*>(smem + G::OFF_AUD);
-  float* w1s = reinterpret_cast<float*>(smem + G::OFF_W1);     // [KT][16] then bias[16]
+  float* w1s = reinterpret_cast<float*>(smem + G::OFF_W1);     // [KT][16]
   double* red = reinterpret_cast<double*>(smem + G::OFF_RED);  // [2][COUT]
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(sbase + BAR_FULL + 8 * b, 8);     // one elected arrival per producer warp
+      mbar_init(sbase + BAR_FULL + 8 * b, FUSE1 ? NPW : NPW / 2);   // one elected arrival per staging warp
       mbar_init(sbase + BAR_EMPTY + 8 * b, 1);    // tcgen05.commit
       mbar_init(sbase + BAR_TFULL + 8 * b, 1);    // tcgen05.commit
       mbar_init(sbase + BAR_TEMPTY + 8 * b, 8);   // one elected arrival per epilogue warp
@@ -281,178 +287,194 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(sbase + TMEM_SLOT, G::NCOLS);
-  // ---- prologue: BatchNorm of the input as scale / shift (CTA 0 updates the running statistics once)
+  // ---- prologue: BatchNorm of the input as scale / shift (CTA 0 updates the running statistics once); the fused first
+  //      layer folds conv1's bias into the shift
   if (tid < CIN) {
     float a, b;
     bn_scale_shift(p.bn, tid, CIN, blockIdx.x == 0, a, b);
+    if (FUSE1) b = fmaf(__ldg(p.b1 + tid), a, b);
     sc[tid] = a; sh[tid] = b;
   }
   for (int i = tid; i < 2 * COUT; i += THREADS) red[i] = 0.0;
-  if (FUSE1) {
+  if (FUSE1)
     for (int i = tid; i < KT * C1; i += THREADS) w1s[i] = __ldg(p.w1 + (i % C1) * KT + i / C1);
-    if (tid < C1) w1s[KT * C1 + tid] = __ldg(p.b1 + tid);
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const float slope = p.bn.slope;   // 0 <= slope <= 1: LeakyReLU(v) = max(v, slope * v)
 
-  if (warp_u < 8) {
+  if (warp_u < NPW) {
     // =================================================================================================== producers
-    auto audio_prefetch = [&](int tile, int abuf) {
-      // audio span of the tile's rows: at most two clips (pitch > R); second clip's span starts at seg1
-      const int a0 = tile * TM;
-      const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
-      const int n0 = min(R, p.pitch - j0);
-      const uint32_t dst = smem_u32(aud + abuf * AUD_FLOATS);
-      const float* src0 = p.x + (long)c0 * p.L;
-      for (int i = tid; i < S1 * S * n0 + KT; i += NPROD) {
-        const int s = S1 * S * j0 - PAD1 + i;
-        const bool ok = s >= 0 && s < p.L;
-        cp_async4(dst + 4u * i, src0 + (ok ? s : 0), ok);
-      }
-      if (n0 < R) {
-        const int n1 = R - n0, seg1 = S1 * S * n0 + 16;
-        const bool clip_ok = c0 + 1 < p.B;
-        const float* src1 = p.x + (long)(clip_ok ? c0 + 1 : c0) * p.L;
-        for (int i = tid; i < S1 * S * n1 + KT; i += NPROD) {
-          const int s = i - PAD1;
-          const bool ok = clip_ok && s >= 0 && s < p.L;
-          cp_async4(dst + 4u * (seg1 + i), src1 + (ok ? s : 0), ok);
-        }
-      }
-    };
     if (FUSE1) {
+      // all staging warps work on the same tile: conv1 (fp32 SIMT, FFMA2) + BN1 + LeakyReLU -> operand images
+      auto audio_prefetch = [&](int tile, int abuf) {
+        // audio span of the tile's rows: at most two clips (pitch > R); second clip's span starts at seg1
+        const int a0 = tile * TM;
+        const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
+        const int n0 = min(R, p.pitch - j0);
+        const uint32_t dst = smem_u32(aud + abuf * AUD_FLOATS);
+        const float* src0 = p.x + (long)c0 * p.L;
+        for (int i = tid; i < S1 * S * n0 + KT; i += NPROD) {
+          const int s = S1 * S * j0 - PAD1 + i;
+          const bool ok = s >= 0 && s < p.L;
+          cp_async4(dst + 4u * i, src0 + (ok ? s : 0), ok);
+        }
+        if (n0 < R) {
+          const int n1 = R - n0, seg1 = S1 * S * n0 + 16;
+          const bool clip_ok = c0 + 1 < p.B;
+          const float* src1 = p.x + (long)(clip_ok ? c0 + 1 : c0) * p.L;
+          for (int i = tid; i < S1 * S * n1 + KT; i += NPROD) {
+            const int s = i - PAD1;
+            const bool ok = clip_ok && s >= 0 && s < p.L;
+            cp_async4(dst + 4u * (seg1 + i), src1 + (ok ? s : 0), ok);
+          }
+        }
+      };
       if (my_tiles > 0) audio_prefetch(blockIdx.x, 0);
       cp_async_commit();
-    }
-    int n = 0;
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int tile = blockIdx.x + tl * gridDim.x;
-      const int a0 = tile * TM;
-      if (FUSE1) {
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int tile = blockIdx.x + tl * gridDim.x;
+        const int a0 = tile * TM;
         cp_async_wait<0>();
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // every producer's copies landed; conv1 of tile tl-1 is done
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");   // every warp's copies landed; conv1 of tile tl-1 is done
         if (tl + 1 < my_tiles) audio_prefetch(tile + gridDim.x, (tl + 1) & 1);
         cp_async_commit();
-      }
-      for (int pass = 0; pass < G::NPASS; ++pass, ++n) {
-        const int buf = n & 1;
-        if (n >= 2) mbar_wait(sbase + BAR_EMPTY + 8 * buf, ((n >> 1) - 1) & 1);
+        const int buf = tl & 1;
+        if (tl >= 2) mbar_wait(sbase + BAR_EMPTY + 8 * buf, ((tl >> 1) - 1) & 1);
         unsigned char* a_hi = a_base + buf * A_BUF;
         unsigned char* a_lo = a_hi + A_PLANE;
-        if (FUSE1) {
-          // ---- conv1 (fp32 SIMT) + BN1 + LeakyReLU -> operand images; thread = 2 pixels x 16 channels at a time
-          const float* au = aud + (tl & 1) * AUD_FLOATS;
-          const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
-          const int n0 = min(R, p.pitch - j0);
-          const int seg1 = S1 * S * n0 + 16;
-          for (int base = 0; base < R * S; base += 2 * NPROD) {
-            if (base + tid >= R * S) break;
-            int off[2], dst[2]; bool ok[2], real[2];
+        const float* au = aud + (tl & 1) * AUD_FLOATS;
+        const int c0 = a0 / p.pitch, j0 = a0 - c0 * p.pitch;
+        const int n0 = min(R, p.pitch - j0);
+        const int seg1 = S1 * S * n0 + 16;
+        // thread = local pixels tid and tid + NPROD (consecutive threads, consecutive pixels: sample stride 5,
+        // conflict-free shared loads); local pixel lp = 6 * row + phase
+        int off[2], dst[2]; bool ok[2], real[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int idx = base + tid + NPROD * i;      // idx = r * R + row: consecutive threads, consecutive rows
-              ok[i] = idx < R * S;
-              const int r = ok[i] ? idx / R : 0, row = ok[i] ? idx - r * R : 0;
-              const bool second = row >= n0;
-              const int j = second ? row - n0 : j0 + row;
-              const int pix = S * j + r;
-              real[i] = ok[i] && (c0 + (second ? 1 : 0)) < p.B && pix < p.Lin;
-              off[i] = real[i] ? (second ? seg1 + S1 * pix : S1 * (pix - S * j0)) : 0;
-              dst[i] = (r * PST + row) * 16;
-            }
-            float acc[2][C1];
+        for (int i = 0; i < 2; ++i) {
+          const int lp = tid + NPROD * i;
+          ok[i] = lp < R * S;
+          const int row = lp / S, r = lp - row * S;
+          const bool second = row >= n0;
+          const int pix = second ? lp - S * n0 : S * j0 + lp;
+          real[i] = ok[i] && (c0 + (second ? 1 : 0)) < p.B && pix < p.Lin;
+          off[i] = real[i] ? (second ? seg1 + S1 * pix : S1 * lp) : 0;
+          dst[i] = (r * PST + row) * 16;
+        }
+        float2 acc[2][C1 / 2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int c = 0; c < C1; ++c) acc[i][c] = 0.f;
+          for (int c = 0; c < C1 / 2; ++c) acc[i][c] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < KT; ++t) {
-              float wv[C1];
+        for (int t = 0; t < KT; ++t) {
+          float2 wv[C1 / 2];
 #pragma unroll
-              for (int c4 = 0; c4 < C1 / 4; ++c4) {
-                const float4 q = *reinterpret_cast<const float4*>(w1s + t * C1 + 4 * c4);
-                wv[4 * c4] = q.x; wv[4 * c4 + 1] = q.y; wv[4 * c4 + 2] = q.z; wv[4 * c4 + 3] = q.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const float xv = au[off[i] + t];
-#pragma unroll
-                for (int c = 0; c < C1; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (!ok[i]) continue;
-#pragma unroll
-              for (int kc = 0; kc < 2; ++kc) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int c = kc * 8 + e;
-                  const float tv = fmaf(acc[i][c] + w1s[KT * C1 + c], sc[c], sh[c]);
-                  v[e] = real[i] ? (tv > 0.f ? tv : tv * p.bn.slope) : 0.f;
-                }
-                uint4 hi, lo;
-                pack8w(v, hi, lo);
-                *reinterpret_cast<uint4*>(a_hi + dst[i] + kc * RC * 16) = hi;
-                if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i] + kc * RC * 16) = lo;
-              }
-            }
+          for (int c4 = 0; c4 < C1 / 4; ++c4) {
+            const float4 q = *reinterpret_cast<const float4*>(w1s + t * C1 + 4 * c4);
+            wv[2 * c4] = make_float2(q.x, q.y); wv[2 * c4 + 1] = make_float2(q.z, q.w);
           }
-        } else {
-          // ---- raw producer output -> BN + LeakyReLU -> operand images; item = (local pixel, 8-channel chunk):
-          //      consecutive threads read consecutive 32-byte segments; 4 items (8 x LDG.128) in flight per thread
-          const int ch0 = pass * 16;
-          constexpr int ITEMS = R * S * 2;
-          for (int base = 0; base < ITEMS; base += 4 * NPROD) {
-            float4 va[4], vb[4]; int dst[4]; bool ok[4], real[4]; int chv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int it = base + tid + NPROD * i;
-              ok[i] = it < ITEMS;
-              const int kc = it & 1, lp = it >> 1;
-              const int row = lp / S, r = lp - row * S;
-              const int g = a0 + row;
-              const int c = g / p.pitch, j = g - c * p.pitch;
-              const int pix = S * j + r;
-              real[i] = ok[i] && c < p.B && pix < p.Lin;
-              chv[i] = ch0 + kc * 8;
-              dst[i] = (r * PST + kc * RC + row) * 16;
-              if (real[i]) {
-                const float4* src = reinterpret_cast<const float4*>(p.x + ((long)c * p.Lin + pix) * CIN + chv[i]);
-                va[i] = __ldg(src); vb[i] = __ldg(src + 1);
-              } else {
-                va[i] = make_float4(0.f, 0.f, 0.f, 0.f); vb[i] = va[i];
-              }
+          for (int i = 0; i < 2; ++i) {
+            const float xv = au[off[i] + t];
+            const float2 x2 = make_float2(xv, xv);
+#pragma unroll
+            for (int c = 0; c < C1 / 2; ++c) acc[i][c] = __ffma2_rn(x2, wv[c], acc[i][c]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (!ok[i]) continue;
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = kc * 8 + e;
+              const float a = (e & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
+              const float tv = fmaf(a, sc[c], sh[c]);
+              v[e] = real[i] ? fmaxf(tv, tv * slope) : 0.f;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (!ok[i]) continue;
-              float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
-              if (real[i]) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float tv = fmaf(v[e], sc[chv[i] + e], sh[chv[i] + e]);
-                  v[e] = tv > 0.f ? tv : tv * p.bn.slope;
-                }
-              }
-              uint4 hi, lo;
-              pack8w(v, hi, lo);
-              *reinterpret_cast<uint4*>(a_hi + dst[i]) = hi;
-              if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i]) = lo;
-            }
+            uint4 hi, lo;
+            pack8w(v, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + dst[i] + kc * RC * 16) = hi;
+            if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i] + kc * RC * 16) = lo;
           }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cta(sbase + BAR_FULL + 8 * buf);
       }
+      cp_async_wait<0>();
+    } else {
+      // two staging groups of NPW/2 warps: group g stages the items n = g (mod 2) into buffer g, so the loads of one
+      // item are in flight while the other group converts (raw producer output -> BN + LeakyReLU -> operand images).
+      // item = (local pixel, 8-channel chunk): consecutive threads read consecutive 32-byte segments
+      constexpr int GT = (NPW / 2) * 32;                  // threads per group
+      constexpr int ITEMS = R * S * 2;
+      constexpr int PER = (ITEMS + GT - 1) / GT;          // items per thread (7)
+      const int g = warp_u >= NPW / 2 ? 1 : 0, gtid = tid - g * GT;
+      unsigned char* a_hi = a_base + g * A_BUF;
+      unsigned char* a_lo = a_hi + A_PLANE;
+      const int n_items = my_tiles * G::NPASS;
+      int use = 0;
+      for (int n = g; n < n_items; n += 2, ++use) {
+        const int tl = n / G::NPASS, pass = n - tl * G::NPASS;
+        const int a0 = (blockIdx.x + tl * gridDim.x) * TM;
+        const int ch0 = pass * 16;
+        if (use >= 1) mbar_wait(sbase + BAR_EMPTY + 8 * g, (use - 1) & 1);
+#pragma unroll
+        for (int b0 = 0; b0 < PER; b0 += 4) {
+          float4 va[4], vb[4]; int dst[4]; bool ok[4], real[4]; int chv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int it = gtid + GT * (b0 + i);
+            ok[i] = (b0 + i < PER) && it < ITEMS;
+            const int kc = it & 1, lp = it >> 1;
+            const int row = lp / S, r = lp - row * S;
+            const int gr = a0 + row;
+            const int c = gr / p.pitch, j = gr - c * p.pitch;
+            const int pix = S * j + r;
+            real[i] = ok[i] && c < p.B && pix < p.Lin;
+            chv[i] = ch0 + kc * 8;
+            dst[i] = (r * PST + kc * RC + row) * 16;
+            if (real[i]) {
+              const float4* src = reinterpret_cast<const float4*>(p.x + ((long)c * p.Lin + pix) * CIN + chv[i]);
+              va[i] = __ldg(src); vb[i] = __ldg(src + 1);
+            } else {
+              va[i] = make_float4(0.f, 0.f, 0.f, 0.f); vb[i] = va[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!ok[i]) continue;
+            float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+            if (real[i]) {
+              const float4* s4 = reinterpret_cast<const float4*>(sc + chv[i]);
+              const float4* h4 = reinterpret_cast<const float4*>(sh + chv[i]);
+              const float4 s0 = s4[0], s1v = s4[1], h0 = h4[0], h1 = h4[1];
+              const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+              const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float tv = fmaf(v[e], scv[e], shv[e]);
+                v[e] = fmaxf(tv, tv * slope);
+              }
+            }
+            uint4 hi, lo;
+            pack8w(v, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + dst[i]) = hi;
+            if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst[i]) = lo;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(sbase + BAR_FULL + 8 * g);
+      }
     }
-    if (FUSE1) cp_async_wait<0>();
-  } else if (warp_u == 8) {
+  } else if (warp_u == NPW) {
     // ====================================================================================================== issuer
     if (elect_one()) {
       // the layer's whole weight image: one expect_tx, bulk copies of <= 32 KB
@@ -493,12 +515,12 @@ __global__ void __launch_bounds__(THREADS, 1) wav_conv_kernel(Params p) {
     }
   } else {
     // ==================================================================================================== epilogue
-    // warps 9..16: TMEM lane quadrant = warp & 3, channel half = (warp - 9) >> 2
+    // 8 warps: TMEM lane quadrant = warp & 3 (hardware rule), channel half = (warp - NPW - 1) >> 2
     constexpr int CH = COUT / 2;
     float s1[CH], s2[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) s1[c] = s2[c] = 0.f;
-    const int quad = warp & 3, half = (warp - 9) >> 2;
+    const int quad = warp & 3, half = (warp - NPW - 1) >> 2;
     const int c_beg = half * CH;
     const bool vec_dst = (p.ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
@@ -610,6 +632,7 @@ extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float
   const int L4 = conv_len(L3, KT, S, 0);
   S2AG_CHECK_ARG(ldy >= 32 && (long)B * L1 < (1L << 31) && (long)B * L < (1L << 40));
   S2AG_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 31) == 0);
+  S2AG_CHECK_ARG(slope >= 0.f && slope <= 1.f);   // LeakyReLU evaluated as max(v, slope * v)
   cudaStream_t st = (cudaStream_t)stream;
   static int sms = 0;
   if (!sms) {
