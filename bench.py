@@ -148,7 +148,10 @@ def run_reference_arm(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same shapes (profiles/,
 # 256 clips); None where no capture of that kernel is committed
 NCU_TRAFFIC = {"gru_recurrence_fwd": 66.0e6 + 55.6e6,   # profiles/r01_ncu_gru_persist.txt
-               "gemm_gru_projection": 38848512}         # profiles/r01_ncu_gemm_umma_pk.txt
+               "gemm_gru_projection": 38848512,         # profiles/r01_ncu_gemm_umma_pk.txt
+               # profiles/r02_ncu_wavencoder.txt: sum over the four launches (ncu flushes L2 between kernels, so the
+               # raw conv2/conv3 intermediates -- L2-resident in a real step -- are counted as DRAM reads here)
+               "wavencoder_fwd": 37.45e6 + (37.22e6 + 2.99e6) + (43.21e6 + 0.42e6) + 14.39e6}
 
 
 def _time_call(torch, call, flush, reps=10, warm=3):
@@ -234,8 +237,9 @@ def roofline(B, dev, lib, clips_per_s_per_gpu=None):
     audio = torch.rand(B, AUDIO_LEN, device=dev) - 0.5
     with torch.no_grad():
         ms = _time_call(torch, lambda: we(audio), flush, reps=5)
-    entry("wavencoder_fwd", "WavEncoder.forward (conv1 direct + strided convs on the tcgen05 engine, BatchNorm fused "
-          "as built)", "hbm", ms, 39.38e6 * B, 149420.0 * B)
+    entry("wavencoder_fwd", "wav_prep_kernel + wav_conv_kernel<16,32,1> + <32,64,0> + <64,32,0> (umma_wav.cu: conv1 "
+          "recomputed per tile, BatchNorm + LeakyReLU applied while the next strided convolution stages its tcgen05 "
+          "operand, train-mode batch statistics)", "hbm", ms, 39.38e6 * B, 149420.0 * B)
     r = dict(dom)
     r["roofline_kernels"] = out
     if clips_per_s_per_gpu is not None:
