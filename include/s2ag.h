@@ -145,6 +145,18 @@ int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy, const int3
                 float* dx, long lddx, float* dgamma, float* dbeta, float* dadd, long lddadd,
                 double* ws, int groups, void* stream);
 
+/* ---- causal-TCN residual block forward as ONE kernel (net/tcn.py:16-46; umma_tcn.cu): same semantics and dropout
+ * streams as s2ag_weight_norm_fwd x2 + s2ag_tcn_block_fwd, but y1 stays on the SM (conv2 consumes it from shared
+ * memory) and weight_norm is folded into the operand packing.  v1,g1,b1 / v2,g2,b2: weight_norm parameters ([C][C][2], [C], [C]);
+ * w1/w2 [C][2][C] and n1/n2 [C] receive the effective fp32 weights and norms (inputs of s2ag_tcn_block_bwd /
+ * s2ag_weight_norm_bwd); y1 / y2 may be NULL when no backward pass follows; ws: s2ag_tcn_fused_ws_floats(T, C, dilation)
+ * floats, 16-byte aligned (0 = shape not covered: use the two-launch entry).  Whole clips per CTA: T + dilation <= 128. */
+long s2ag_tcn_fused_ws_floats(int T, int C, int dilation);
+int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const float* g1, const float* b1, const float* v2,
+                             const float* g2, const float* b2, float* w1, float* w2, float* n1, float* n2, float* y1,
+                             float* y2, float* out, float* ws, int B, int T, int C, int dilation, float p_drop,
+                             uint64_t seed, const uint64_t* seed_dev, void* stream);
+
 /* ---- fused WavEncoder forward (net/multimodal_context_net_v2.py:14-33; frozen inside PoseGeneratorTriModal :277,
  * called at :301) -- raw audio [B, L] -> features y[B, 34, 32] (row stride ldy floats), replacing the chain
  * Conv1d(1,16,15,s5,p1600) BN LReLU Conv1d(16,32,15,s6) BN LReLU Conv1d(32,64,15,s6) BN LReLU Conv1d(64,32,15,s6).

@@ -83,6 +83,18 @@ extern "C" int s2ag_debug_flags(int flags) {
 }
 #ifdef S2AG_EMU
 extern "C" int s2ag_debug_gru_cluster_occupancy(int H, int backward) { (void)H; (void)backward; return S2AG_ERR_UNSUPPORTED; }
+// umma_tcn.cu (tcgen05): the emulation build reports "shape not covered", the host mirror then uses the two-launch path
+extern "C" long s2ag_tcn_fused_ws_floats(int T, int C, int dilation) { (void)T; (void)C; (void)dilation; return 0; }
+extern "C" int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const float* g1, const float* b1, const float* v2,
+                                        const float* g2, const float* b2, float* w1, float* w2, float* n1, float* n2,
+                                        float* y1, float* y2, float* out, float* ws, int B, int T, int C, int dilation,
+                                        float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  (void)x; (void)v1; (void)g1; (void)b1; (void)v2; (void)g2; (void)b2; (void)w1; (void)w2; (void)n1; (void)n2; (void)y1;
+  (void)y2; (void)out; (void)ws; (void)B; (void)T; (void)C; (void)dilation; (void)p_drop; (void)seed; (void)seed_dev;
+  (void)stream;
+  s2ag_set_error("s2ag_tcn_block_fused_fwd: device build only");
+  return S2AG_ERR_UNSUPPORTED;
+}
 // umma_wav.cu (tcgen05) is not part of the emulation build: the host mirror uses the unfused chain there
 extern "C" long s2ag_wavencoder_ws_floats(int B, int L) { (void)B; (void)L; return 0; }
 extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float* const* conv_w, const float* const* conv_b,

@@ -10,6 +10,7 @@ flat buffer per network), so the backward functions return None for parameters.
 """
 import ctypes
 import itertools
+import os
 
 import torch
 
@@ -580,6 +581,13 @@ def dropout(x, p, training):
 
 
 # ------------------------------------------------------------------------------------------ TCN residual block
+# Single-kernel TCN block (csrc/umma_tcn.cu) vs two conv-as-GEMM launches (csrc/tcn.cu).  Measured at 256 clips (B200):
+# 74 us + 7 us packing on 86 SMs against 2 x 34 us + 17 us weight_norm/packing on 136 SMs, and 13.80 vs 13.50 ms per GAN
+# step -- the fused kernel is bound by streaming the 1.5 MB weight image through every SM, so the two-launch
+# path stays the default; S2AG_TCN_FUSED=1 selects the fused kernel (parity-tested either way).
+TCN_FUSED = [os.environ.get("S2AG_TCN_FUSED", "0") == "1"]
+
+
 class TcnBlockFn(torch.autograd.Function):
     """weight_norm + TemporalBlock (net/tcn.py:16-46) over channels-last x[B,T,C]."""
 
@@ -594,12 +602,25 @@ class TcnBlockFn(torch.autograd.Function):
         st = _stream(x)
         w1, w2 = _empty((C, k, C), x), _empty((C, k, C), x)
         n1, n2 = _empty((C,), x), _empty((C,), x)
-        _C.call("s2ag_weight_norm_fwd", _p(v1), _p(g1), _p(w1), _p(n1), C, C, k, st)
-        _C.call("s2ag_weight_norm_fwd", _p(v2), _p(g2), _p(w2), _p(n2), C, C, k, st)
-        y1, y2, out = _empty(x.shape, x), _empty(x.shape, x), _empty(x.shape, x)
+        out = _empty(x.shape, x)
         nonce = seed_nonce(x.device) if p > 0 else None
-        _C.call("s2ag_tcn_block_fwd", _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y1), _p(y2), _p(out), B, T, C, dilation,
-                float(p), ctypes.c_uint64(seed), _p(nonce), st)
+        n_ws = 0 if (_C.is_emulated() or not TCN_FUSED[0]) else _C.lib().s2ag_tcn_fused_ws_floats(T, C, dilation)
+        if n_ws > 0:
+            # one kernel per block (csrc/umma_tcn.cu): y1 stays in shared memory; it and y2 reach HBM only when a
+            # backward pass will read them
+            need_bwd = any(ctx.needs_input_grad)
+            y1 = _empty(x.shape, x) if need_bwd else None
+            y2 = _empty(x.shape, x) if need_bwd else None
+            ws = _empty((n_ws,), x)
+            _C.call("s2ag_tcn_block_fused_fwd", _p(x), _p(v1), _p(g1), _p(b1), _p(v2), _p(g2), _p(b2), _p(w1), _p(w2),
+                    _p(n1), _p(n2), _p(y1), _p(y2), _p(out), _p(ws), B, T, C, dilation, float(p), ctypes.c_uint64(seed),
+                    _p(nonce), st)
+        else:
+            _C.call("s2ag_weight_norm_fwd", _p(v1), _p(g1), _p(w1), _p(n1), C, C, k, st)
+            _C.call("s2ag_weight_norm_fwd", _p(v2), _p(g2), _p(w2), _p(n2), C, C, k, st)
+            y1, y2 = _empty(x.shape, x), _empty(x.shape, x)
+            _C.call("s2ag_tcn_block_fwd", _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y1), _p(y2), _p(out), B, T, C,
+                    dilation, float(p), ctypes.c_uint64(seed), _p(nonce), st)
         ctx.t = (x, y1, y2, out.detach(), w1, w2, n1, n2, v1, g1, b1, v2, g2, b2)
         ctx.cfg = (B, T, C, k, dilation, float(p))
         ctx.want_w = v1.requires_grad

@@ -456,3 +456,56 @@ def test_no_reference_cycles(dev):
             assert r() is None, "reference cycle through the output of %s" % name
     finally:
         gc.enable()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,C,d,p", [(7, 34, 300, 1, 0.0), (7, 34, 300, 8, 0.3), (2, 100, 300, 8, 0.3), (5, 34, 24, 4, 0.2),
+                                        (150, 34, 300, 2, 0.3)])
+def test_tcn_block_fused_vs_two_launch(B, T, C, d, p):
+    """single-kernel TCN block (csrc/umma_tcn.cu) against the two conv-as-GEMM launches (csrc/tcn.cu) from the same
+    dropout seed (identical masks): output, saved activations through the backward pass, all parameter gradients.
+    Covers the column split of the accumulator (C = 300 -> 160 + 144), partial last tiles, one clip per tile."""
+    dev = torch.device("cuda:0")
+    from speech2affective_gestures_b200 import _C
+    if _C.is_emulated():
+        _C._lib, _C._emulated = None, False
+    torch.manual_seed(21)
+    raw = [torch.randn(C, C, 2) * 0.08, torch.rand(C, 1, 1) + 0.5, torch.randn(C) * 0.1,
+           torch.randn(C, C, 2) * 0.08, torch.rand(C, 1, 1) + 0.5, torch.randn(C) * 0.1]
+    x = torch.randn(B, T, C)
+    g = torch.randn(B, T, C)
+    res = {}
+    default = ops.TCN_FUSED[0]
+    for fused in (True, False):
+        ops.TCN_FUSED[0] = fused
+        try:
+            ps = [P(t, dev) for t in raw]
+            xd = P(x, dev)
+            ops.manual_seed(77)
+            y = ops.tcn_block(xd, *ps, d, p, training=True)
+            y.backward(g.to(dev))
+            res[fused] = [y.detach(), xd.grad] + [q.grad for q in ps]
+        finally:
+            ops.TCN_FUSED[0] = default
+    if p > 0:
+        assert 0.02 < (res[True][0] == 0).float().mean().item() < 0.98
+    names = ("out", "dx", "dv1", "dg1", "db1", "dv2", "dg2", "db2")
+    close(res[True][0], res[False][0], what="out")
+    if B * T * C > 200000:
+        # two fp32-grade summation orders: a few of the ~1e6 ReLU inputs land on the other side of 0 and each flip
+        # moves single gradient elements by O(1) -- the flip-robust criteria of the module tests (common.check_grads)
+        from common import check_grads
+        check_grads(dict(zip(names[1:], res[True][1:])), dict(zip(names[1:], res[False][1:])), tol=2e-3, what="fused TCN")
+    else:
+        for a, b, nm in zip(res[True][1:], res[False][1:], names[1:]):
+            close(a, b, what=nm)
+    # no-grad call (y1 / y2 never written): same output
+    ps = [t.to(dev) for t in raw]
+    ops.manual_seed(77)
+    ops.TCN_FUSED[0] = True
+    try:
+        with torch.no_grad():
+            y0 = ops.tcn_block(x.to(dev), *ps, d, p, training=True)
+    finally:
+        ops.TCN_FUSED[0] = default
+    close(y0, res[True][0], what="no-grad out")

@@ -9,7 +9,7 @@ void s2ag_set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfpri
 namespace s2ag { int g_engine = 0; namespace umma { int g_precision = 0; int g_dbg_flags = 0; } }
 using namespace s2ag::umma;
 
-template <int N, int NACC, bool BMN>
+template <int N, int NACC, bool BMN, int AROWS = 128, int ASHIFT = 0>
 __global__ void __launch_bounds__(128, 1) probe(int R, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(128, 1) probe(int R, long long* out) {
   const uint32_t bar = sbase;
   volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + 16);
   unsigned char* a = smem + 1024;              // A: K-major [k-chunk][128][16], 16 k-chunks
-  unsigned char* b = a + 16 * 128 * 16;        // B: K-major [k-chunk][256][16] or MN-major [group of 8][k rows][16]
-  for (int i = tid; i < (16 * 128 * 16 + 16 * 256 * 16) / 16; i += 128) reinterpret_cast<uint4*>(a)[i] = make_uint4(0, 0, 0, 0);
+  unsigned char* b = a + 16 * 144 * 16;        // B: K-major [k-chunk][256][16] or MN-major [group of 8][k rows][16]
+  for (int i = tid; i < (16 * 144 * 16 + 16 * 256 * 16) / 16; i += 128) reinterpret_cast<uint4*>(a)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) tmem_alloc(sbase + 16, 512);
   fence_async_smem();
@@ -29,9 +29,9 @@ __global__ void __launch_bounds__(128, 1) probe(int R, long long* out) {
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   if (warp_u == 1 && elect_one()) {
     const uint32_t idesc = make_idesc(N) | (BMN ? (1u << 16) : 0u);
-    const uint64_t da0 = make_desc(smem_u32(a), 128 * 16, 128);
+    const uint64_t da0 = make_desc(smem_u32(a) + ASHIFT * 16, AROWS * 16, 128);   // AROWS: chunk stride in rows, ASHIFT: row shift
     const uint64_t db0 = BMN ? make_desc(smem_u32(b), 128, 128 * 16) : make_desc(smem_u32(b), 256 * 16, 128);
-    constexpr uint32_t astep = (2 * 128 * 16) >> 4, bstep = BMN ? (256 >> 4) : ((2 * 256 * 16) >> 4);
+    constexpr uint32_t astep = (2 * AROWS * 16) >> 4, bstep = BMN ? (256 >> 4) : ((2 * 256 * 16) >> 4);
     for (int rep = 0; rep < 3; ++rep) {
       const long long t0 = clock64();
       for (int it = 0; it < R / 8; ++it) {
@@ -52,15 +52,15 @@ __global__ void __launch_bounds__(128, 1) probe(int R, long long* out) {
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
-template <int N, int NACC, bool BMN>
+template <int N, int NACC, bool BMN, int AROWS = 128, int ASHIFT = 0>
 static void run(long long* d, int R) {
-  auto k = &probe<N, NACC, BMN>;
+  auto k = &probe<N, NACC, BMN, AROWS, ASHIFT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k<<<1, 128, 1024 + 16 * 128 * 16 + 16 * 256 * 16>>>(R, d);
+  k<<<1, 128, 1024 + 16 * 144 * 16 + 16 * 256 * 16>>>(R, d);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
   long long h[6];
   cudaMemcpy(h, d, 48, cudaMemcpyDeviceToHost);
-  printf("  B %s  N=%3d  nacc=%d : issue %6.1f  total %6.1f\n", BMN ? "MN-major" : "K-major ", N, NACC, h[4] / (double)R, h[5] / (double)R);
+  printf("  B %s  N=%3d  nacc=%d  A chunk stride %d rows, start row %d : issue %6.1f  total %6.1f\n", BMN ? "MN-major" : "K-major ", N, NACC, AROWS, ASHIFT, h[4] / (double)R, h[5] / (double)R);
 }
 
 int main() {
@@ -70,6 +70,7 @@ int main() {
   run<16, 1, false>(d, R); run<32, 1, false>(d, R); run<32, 2, false>(d, R); run<32, 4, false>(d, R);
   run<48, 1, false>(d, R); run<48, 4, false>(d, R); run<64, 1, false>(d, R); run<64, 2, false>(d, R); run<64, 4, false>(d, R);
   run<128, 1, false>(d, R); run<128, 2, false>(d, R); run<256, 1, false>(d, R); run<256, 2, false>(d, R);
+  run<144, 1, false>(d, R); run<160, 1, false>(d, R); run<160, 1, false, 137, 0>(d, R); run<160, 1, false, 137, 2>(d, R); run<160, 1, false, 136, 2>(d, R); run<160, 1, false, 136, 8>(d, R); run<64, 1, false, 132, 1>(d, R);
   run<32, 1, true>(d, R); run<32, 4, true>(d, R); run<64, 1, true>(d, R); run<64, 2, true>(d, R); run<128, 2, true>(d, R); run<256, 2, true>(d, R);
   return 0;
 }
