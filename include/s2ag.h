@@ -56,7 +56,8 @@ int s2ag_set_precision(int mode);
  *   256 no packed-weight route: both operands of every contraction are converted on the fly
  *   1024 L2-exchange GRU forward (umma_gru.cu) also where the cluster kernel (umma_gru_cluster.cu) is the default
  *   2048 cluster GRU forward for every supported hidden size (default: H <= 80; see umma_gru_cluster.cu)
- *   4096 cluster GRU forward: wait for every h slice before the first tcgen05.mma of a step (measurement) */
+ *   4096 cluster GRU forward: wait for every h slice before the first tcgen05.mma of a step (measurement)
+ *   8192 fused TCN block: CTA-pair variant (tcgen05 cta_group::2, M = 256; measured slower than one CTA per tile) */
 int s2ag_debug_flags(int flags);
 /* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
  * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */

@@ -31,8 +31,38 @@ namespace tcnf {
 
 using namespace s2ag::umma;
 
-constexpr int TM = 128, NWW = 16, NWORK = NWW * 32, THREADS = NWORK + 64, NSTAGE = 5, HDR = 1024;   // 16 worker warps + issuer + TMA
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 40, BAR_ACC = 80, BAR_AREADY = 96, TMEM_SLOT = 112;   // BAR_ACC: one per column half
+constexpr int TM = 128, NWW = 16, NWORK = NWW * 32, THREADS = NWORK + 64, HDR = 1024;   // 16 worker warps + issuer + TMA
+constexpr int NSTAGE_1 = 5, NSTAGE_2 = 8;    // weight-ring slots: single CTA (10 KB each) / CTA pair (5 KB each; one relay warp per slot)
+// mbarriers (8 bytes each): weights landed (own copy) | ring slot free | weights landed in the peer CTA (pair leader only) |
+// accumulator column half complete | operand image staged
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 128, BAR_PFULL = 256, BAR_ACC = 384, BAR_AREADY = 400, TMEM_SLOT = 416;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// CTA-pair forms (semantics checked by tools/mma2_probe.cu): M = 256 over the pair, each CTA supplies its 128 rows of A and
+// its half of B's rows from the SAME shared-memory offsets; the commit arrives on the barrier at that offset in both CTAs
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_pair(int n) {   // M = 256
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 
 struct Params {
   const float* x; const float* b1; const float* b2;
@@ -74,7 +104,7 @@ __global__ void __launch_bounds__(128) tcn_pack_kernel(const float* __restrict__
                                                        const float* __restrict__ v2, const float* __restrict__ g2,
                                                        float* __restrict__ w1, float* __restrict__ w2,
                                                        float* __restrict__ n1, float* __restrict__ n2,
-                                                       unsigned char* __restrict__ wpk, int C, int Cpad, int KS, int N0) {
+                                                       unsigned char* __restrict__ wpk, int C, int Cpad, int KS, int N0, int pair) {
   __shared__ float red[4];
   __shared__ float wrow[2 * 328];
   const int n = blockIdx.x, conv = blockIdx.y, tid = threadIdx.x;
@@ -112,9 +142,18 @@ __global__ void __launch_bounds__(128) tcn_pack_kernel(const float* __restrict__
     for (int e = 0; e < 8; ++e) vals[e] = wrow[j * 328 + s * 16 + q * 8 + e];
     uint4 hi, lo;
     pack8t(vals, hi, lo);
-    unsigned char* dst = img + (long)(j * KS + s) * stage_bytes + ((long)q * Nh + nn) * 16;
+    unsigned char* dst;
+    long plane;
+    if (pair) {   // [CTA c][plane][chunk q][Nh/2 rows][16 B]: CTA c of a pair holds rows [c Nh/2, (c+1) Nh/2)
+      const int hr = Nh / 2, c = nn / hr, r = nn - c * hr;
+      plane = 2L * hr * 16;
+      dst = img + (long)(j * KS + s) * stage_bytes + (long)c * (stage_bytes / 2) + ((long)q * hr + r) * 16;
+    } else {
+      plane = 2L * Nh * 16;
+      dst = img + (long)(j * KS + s) * stage_bytes + ((long)q * Nh + nn) * 16;
+    }
     *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + 2L * Nh * 16) = lo;
+    *reinterpret_cast<uint4*>(dst + plane) = lo;
   }
 }
 
@@ -125,14 +164,17 @@ __device__ long long g_tcn_tl[3][16];   // [worker | issuer | producer][mark]: c
 #define TCN_MARK(role, slot) do { } while (0)
 #endif
 
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
+  constexpr int NSTAGE = PAIR ? NSTAGE_2 : NSTAGE_1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // PAIR: 2-CTA cluster, rank 0 issues the MMAs for both
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t sbase = smem_u32(smem);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TMEM_SLOT);
   const int a_plane = p.Kc * p.RCH * 16;
-  const int stage_slot = 2 * 2 * p.N0 * 16;   // ring slot = the larger (first) column half's stage
+  const int stage_slot = (2 * 2 * p.N0 * 16) / (PAIR ? 2 : 1);   // ring slot = this CTA's share of the larger column half's stage
   float* bias_s = reinterpret_cast<float*>(smem + HDR);            // b1[Cpad], b2[Cpad]
   unsigned char* a_hi = smem + HDR + 2 * p.Cpad * 4;
   unsigned char* a_lo = a_hi + a_plane;
@@ -140,13 +182,22 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
   const int LEAD = p.d;
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(sbase + BAR_WFULL + 8 * s, 1); mbar_init(sbase + BAR_WEMPTY + 8 * s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(sbase + BAR_WFULL + 8 * s, 1); mbar_init(sbase + BAR_WEMPTY + 8 * s, 1); mbar_init(sbase + BAR_PFULL + 8 * s, 1);
+    }
     mbar_init(sbase + BAR_ACC, 1);
     mbar_init(sbase + BAR_ACC + 8, 1);
-    mbar_init(sbase + BAR_AREADY, NWW);
+    mbar_init(sbase + BAR_AREADY, PAIR ? 2 * NWW : NWW);   // PAIR: the leader's barrier also collects the peer's workers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(sbase + TMEM_SLOT, 512);
+  if (warp == 0) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TMEM_SLOT), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(sbase + TMEM_SLOT, 512);
+    }
+  }
   for (int i = tid; i < 2 * p.Cpad; i += THREADS) {
     const int c = i % p.Cpad;
     bias_s[i] = c < p.C ? __ldg((i < p.Cpad ? p.b1 : p.b2) + c) : 0.f;
@@ -160,9 +211,14 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // PAIR: both CTAs of a pair run the same number of tiles (the odd one out is an empty tile: clips beyond the batch)
+  const int units = PAIR ? (p.tiles + 1) / 2 : p.tiles, unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int my_tiles = units > unit0 ? (units - 1 - unit0) / ustride + 1 : 0;
+  const uint32_t aready_bar = PAIR ? mapa(sbase + BAR_AREADY, 0u) : 0u;   // the leader's "images staged" barrier
   const int n_steps = 2 * p.KS;   // k-steps (stages) per convolution
 
   if (warp_u < NWW) {
@@ -174,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
     const int row = quad * 32 + lane;                 // anchor row of the epilogues (TMEM lane)
     const int gcl = row / p.pitch, t = row - gcl * p.pitch;
     for (int tl = 0; tl < my_tiles; ++tl) {
-      const int tile = blockIdx.x + tl * gridDim.x;
+      const int tile = PAIR ? 2 * (unit0 + tl * ustride) + (int)rank : (int)blockIdx.x + tl * (int)gridDim.x;
       const int clip0 = tile * p.G;
       // ---- x -> operand image (item = (row, chunk), chunk fastest: coalesced 32-byte reads; RCH odd: conflict-free)
       const bool vec_x = (p.C & 3) == 0;
@@ -213,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(sbase + BAR_AREADY);
+      if (lane == 0) { if (PAIR) mbar_arrive_remote(aready_bar); else mbar_arrive_cta(sbase + BAR_AREADY); }
       const bool valid = gcl < p.G && t < p.T && clip0 + gcl < p.B;
       const long grow = ((long)(clip0 + gcl) * p.T + t) * p.C;     // global element offset of this row
       const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -223,12 +279,32 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       const int h_beg = half ? split : 0, h_end = half ? nch : split;          // this half's chunks, then its two quarters
       const int h_mid = h_beg + (h_end - h_beg + 1) / 2;
       const int ch_beg = (part & 1) ? h_mid : h_beg, ch_end = (part & 1) ? h_end : h_mid;
+      // peer CTA of a pair: the leader's issuer must know that THIS CTA's share of a ring item has landed.  Worker warps
+      // 8..15 (column half 1: they wait for the end of either convolution anyway) each relay one ring slot: wait for the
+      // local "landed" barrier, arrive on the leader's PFULL barrier of that slot.  (One thread relaying all slots costs
+      // ~850 cycles per item, lanes of one warp polling different barriers serialise on mbarrier.try_wait.)
+      auto relay = [&](int conv) {
+        if (!PAIR || rank != 1 || warp < NWW / 2) return;
+        const int slot = warp - NWW / 2;
+        const int per_conv = (p.N1 > 0 ? 2 : 1) * n_steps;
+        const int n_beg = (tl * 2 + conv) * per_conv, n_end = n_beg + per_conv;
+        if (lane == 0) {
+          const uint32_t remote = mapa(sbase + BAR_PFULL + 8 * slot, 0u);
+          int n = n_beg + ((slot - n_beg) % NSTAGE + NSTAGE) % NSTAGE;      // first item of this conv in my slot
+          for (; n < n_end; n += NSTAGE) {
+            mbar_wait(sbase + BAR_WFULL + 8 * slot, (n / NSTAGE) & 1);
+            mbar_arrive_remote(remote);
+          }
+        }
+        __syncwarp();
+      };
       // conv1's epilogue overwrites the x image that BOTH column halves of conv1 read: it waits for the last half.
       // conv2's epilogue only writes global memory: half 0 starts as soon as its columns are complete.
       const uint32_t acc_bar1 = sbase + BAR_ACC + (p.N1 > 0 ? 8 : 0);
       const uint32_t acc_bar2 = sbase + BAR_ACC + ((p.N1 > 0 && half) ? 8 : 0);
       // ---- epilogue 1: y1 = drop(relu(acc + b1)) -> operand image of conv2 (zeros in the padding rows)
       if (warp == 0) TCN_MARK(0, 1);
+      relay(0);
       mbar_wait(acc_bar1, 0u);
       if (warp == 0) TCN_MARK(0, 2);
       tc_fence_after();
@@ -262,9 +338,10 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(sbase + BAR_AREADY);
+      if (lane == 0) { if (PAIR) mbar_arrive_remote(aready_bar); else mbar_arrive_cta(sbase + BAR_AREADY); }
       // ---- epilogue 2: y2 = drop(relu(acc + b2)); out = relu(y2 + x)
       if (warp == 0) TCN_MARK(0, 3);
+      relay(1);
       mbar_wait(acc_bar2, 1u);
       if (warp == 0) TCN_MARK(0, 4);
       tc_fence_after();
@@ -324,41 +401,59 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
   } else if (warp_u == NWW) {
     // ====================================================================================================== issuer
     if (elect_one()) {
-      const uint32_t idesc0 = make_idesc(p.N0), idesc1 = make_idesc(p.N1 > 0 ? p.N1 : 16);
-      uint32_t n = 0, aphase = 0;
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        for (int conv = 0; conv < 2; ++conv) {
-          TCN_MARK(1, conv * 4);
-          mbar_wait(sbase + BAR_AREADY, aphase); aphase ^= 1u;
-          TCN_MARK(1, conv * 4 + 1);
-          tc_fence_after();
-          for (int hN = 0; hN < 2; ++hN) {
-            const int Nh = hN ? p.N1 : p.N0;
-            if (Nh > 0) {
-              const uint32_t d = tmem_base + (hN ? (uint32_t)p.N0 : 0u);
-              const uint32_t idesc = hN ? idesc1 : idesc0;
-              const uint32_t plane = (uint32_t)(2 * Nh * 16);
-              for (int ks = 0; ks < n_steps; ++ks, ++n) {
-                const int stage = n % NSTAGE;
-                mbar_wait(sbase + BAR_WFULL + 8 * stage, (n / NSTAGE) & 1);
-                tc_fence_after();
-                const int j = ks / p.KS, s = ks - j * p.KS;           // tap (0: t - d, 1: t), 16-channel group
-                const uint32_t ah = smem_u32(a_hi) + (uint32_t)((2 * s * p.RCH + LEAD - (j == 0 ? p.d : 0)) * 16);
-                const uint32_t al = ah + (uint32_t)a_plane;
-                const uint32_t wh = smem_u32(wst) + (uint32_t)(stage * stage_slot), wl = wh + plane;
-                const uint64_t dah = make_desc(ah, p.RCH * 16, 128), dwh = make_desc(wh, Nh * 16, 128);
-                if (p.x3) {
-                  mma_bf16(d, make_desc(al, p.RCH * 16, 128), dwh, idesc, ks ? 1u : 0u);
-                  mma_bf16(d, dah, make_desc(wl, Nh * 16, 128), idesc, 1u);
-                  mma_bf16(d, dah, dwh, idesc, 1u);
-                } else {
-                  mma_bf16(d, dah, dwh, idesc, ks ? 1u : 0u);
+      if (!PAIR || rank == 0) {
+        const uint32_t idesc0 = PAIR ? make_idesc_pair(p.N0) : make_idesc(p.N0);
+        const uint32_t idesc1 = PAIR ? make_idesc_pair(p.N1 > 0 ? p.N1 : 16) : make_idesc(p.N1 > 0 ? p.N1 : 16);
+        uint32_t n = 0, aphase = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+          for (int conv = 0; conv < 2; ++conv) {
+            TCN_MARK(1, conv * 4);
+            mbar_wait(sbase + BAR_AREADY, aphase); aphase ^= 1u;
+            TCN_MARK(1, conv * 4 + 1);
+            tc_fence_after();
+            for (int hN = 0; hN < 2; ++hN) {
+              const int Nh = hN ? p.N1 : p.N0;
+              if (Nh > 0) {
+                const int Nl = PAIR ? Nh / 2 : Nh;             // B rows held by one CTA
+                const uint32_t d = tmem_base + (hN ? (uint32_t)p.N0 : 0u);
+                const uint32_t idesc = hN ? idesc1 : idesc0;
+                const uint32_t plane = (uint32_t)(2 * Nl * 16);
+                for (int ks = 0; ks < n_steps; ++ks, ++n) {
+                  const int stage = n % NSTAGE;
+                  mbar_wait(sbase + BAR_WFULL + 8 * stage, (n / NSTAGE) & 1);
+                  if (PAIR) mbar_wait(sbase + BAR_PFULL + 8 * stage, (n / NSTAGE) & 1);   // the peer's share has landed too
+                  tc_fence_after();
+                  const int j = ks / p.KS, s = ks - j * p.KS;           // tap (0: t - d, 1: t), 16-channel group
+                  const uint32_t ah = smem_u32(a_hi) + (uint32_t)((2 * s * p.RCH + LEAD - (j == 0 ? p.d : 0)) * 16);
+                  const uint32_t al = ah + (uint32_t)a_plane;
+                  const uint32_t wh = smem_u32(wst) + (uint32_t)(stage * stage_slot), wl = wh + plane;
+                  const uint64_t dah = make_desc(ah, p.RCH * 16, 128), dwh = make_desc(wh, Nl * 16, 128);
+                  const uint64_t dal = make_desc(al, p.RCH * 16, 128), dwl = make_desc(wl, Nl * 16, 128);
+                  if (PAIR) {
+                    if (p.x3) {
+                      mma_bf16_pair(d, dal, dwh, idesc, ks ? 1u : 0u);
+                      mma_bf16_pair(d, dah, dwl, idesc, 1u);
+                      mma_bf16_pair(d, dah, dwh, idesc, 1u);
+                    } else {
+                      mma_bf16_pair(d, dah, dwh, idesc, ks ? 1u : 0u);
+                    }
+                    mma_commit_pair(sbase + BAR_WEMPTY + 8 * stage);
+                  } else {
+                    if (p.x3) {
+                      mma_bf16(d, dal, dwh, idesc, ks ? 1u : 0u);
+                      mma_bf16(d, dah, dwl, idesc, 1u);
+                      mma_bf16(d, dah, dwh, idesc, 1u);
+                    } else {
+                      mma_bf16(d, dah, dwh, idesc, ks ? 1u : 0u);
+                    }
+                    mma_commit(sbase + BAR_WEMPTY + 8 * stage);
+                  }
                 }
-                mma_commit(sbase + BAR_WEMPTY + 8 * stage);
               }
+              // this column half of the accumulator is complete (in both CTAs of a pair)
+              if (PAIR) mma_commit_pair(sbase + BAR_ACC + 8 * hN); else mma_commit(sbase + BAR_ACC + 8 * hN);
+              TCN_MARK(1, conv * 4 + 2 + hN);
             }
-            mma_commit(sbase + BAR_ACC + 8 * hN);   // this column half of the accumulator is complete
-            TCN_MARK(1, conv * 4 + 2 + hN);
           }
         }
       }
@@ -373,17 +468,20 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
           for (int hN = 0; hN < 2; ++hN) {
             const int Nh = hN ? p.N1 : p.N0;
             if (Nh == 0) continue;
-            const uint32_t sb = (uint32_t)(2 * 2 * Nh * 16);
-            const unsigned char* base = p.wpk + conv * conv_bytes + (hN ? (long)n_steps * (2L * 2 * p.N0 * 16) : 0);
+            const uint32_t sb = (uint32_t)(2 * 2 * Nh * 16);          // stage bytes of the whole column half
+            const uint32_t mine = PAIR ? sb / 2 : sb;                 // this CTA's share (PAIR: its half of the B rows)
+            const unsigned char* base = p.wpk + conv * conv_bytes + (hN ? (long)n_steps * (2L * 2 * p.N0 * 16) : 0) +
+                                        (PAIR ? (long)rank * mine : 0);
             for (int ks = 0; ks < n_steps; ++ks, ++n) {
               const int stage = n % NSTAGE;
               if (n >= NSTAGE) mbar_wait(sbase + BAR_WEMPTY + 8 * stage, ((n / NSTAGE) - 1) & 1);
               const unsigned char* src = base + (long)ks * sb;
               const uint32_t dst = smem_u32(wst) + (uint32_t)(stage * stage_slot);
               const uint32_t bar = sbase + BAR_WFULL + 8 * stage;
-              mbar_expect_tx(bar, sb);
-              bulk_g2s(dst, src, sb / 2, bar);
-              bulk_g2s(dst + sb / 2, src + sb / 2, sb / 2, bar);
+              // ONE bulk copy per item: the copy engine costs ~250-300 cycles per copy plus ~1 cycle per 28 bytes
+              // (measured: two 5 KB copies per item 500 cycles, two 2.5 KB copies 640, one 19.5 KB copy 680)
+              mbar_expect_tx(bar, mine);
+              bulk_g2s(dst, src, mine, bar);
             }
           }
         }
@@ -392,7 +490,12 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (PAIR) {
+    cluster_sync_all();      // both CTAs are done with the pair's tensor memory and with each other's barriers
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  } else if (warp == 0) {
+    tmem_dealloc(tmem_base, 512);
+  }
 }
 
 static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
@@ -405,7 +508,7 @@ static Geom geom(int T, int C, int d) {
   g.N1 = g.Cpad - g.N0;
   g.pitch = T + d; g.G = g.pitch <= TM ? TM / g.pitch : 0;
   g.R = TM + d; g.RCH = g.R | 1;
-  g.smem = HDR + 2 * (size_t)g.Cpad * 4 + 2 * (size_t)g.Kc * g.RCH * 16 + (size_t)NSTAGE * 2 * 2 * g.N0 * 16;
+  g.smem = HDR + 2 * (size_t)g.Cpad * 4 + 2 * (size_t)g.Kc * g.RCH * 16 + (size_t)NSTAGE_1 * 2 * 2 * g.N0 * 16;
   g.wpk_bytes = 2L * 2 * g.KS * (2L * 2 * g.Cpad * 16);
   g.ok = g.G >= 1 && g.Cpad <= 512 && g.N1 <= 256 && g.smem <= 227 * 1024 && C <= 320 && d >= 1;
   return g;
@@ -434,9 +537,14 @@ extern "C" int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const f
   if (!g.ok) { s2ag_set_error("s2ag_tcn_block_fused_fwd: unsupported shape T=%d C=%d d=%d", T, C, dilation); return S2AG_ERR_UNSUPPORTED; }
   if (B == 0) return S2AG_OK;
   unsigned char* wpk = reinterpret_cast<unsigned char*>(ws);
+  const int tiles = (B + g.G - 1) / g.G;
+  // s2ag_debug_flags bit 8192: CTA pairs (tcgen05 cta_group::2, M = 256: each CTA streams only its half of the weight
+  // rows).  Correct (parity-tested) but measured SLOWER than one CTA per tile (24 k vs 19 k cycles per column half): the
+  // leader must learn that the peer's share of a ring item has landed, and that relay hop doubles the ring's round trip.
+  const bool pair = tiles >= 2 && (s2ag::umma::g_dbg_flags & 8192);
   {
     auto kp = &tcn_pack_kernel;
-    S2AG_LAUNCH(kp, dim3(g.Cpad, 2), 128, 0, stream, v1, g1, v2, g2, w1, w2, n1, n2, wpk, C, g.Cpad, g.KS, g.N0);
+    S2AG_LAUNCH(kp, dim3(g.Cpad, 2), 128, 0, stream, v1, g1, v2, g2, w1, w2, n1, n2, wpk, C, g.Cpad, g.KS, g.N0, pair ? 1 : 0);
   }
   static int sms = 0;
   if (!sms) {
@@ -445,20 +553,39 @@ extern "C" int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const f
   }
   Params p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.wpk = wpk; p.y1 = y1; p.y2 = y2; p.out = out;
-  p.B = B; p.T = T; p.C = C; p.d = dilation; p.G = g.G; p.pitch = g.pitch; p.tiles = (B + g.G - 1) / g.G;
+  p.B = B; p.T = T; p.C = C; p.d = dilation; p.G = g.G; p.pitch = g.pitch; p.tiles = tiles;
   p.Kc = g.Kc; p.Cpad = g.Cpad; p.KS = g.KS; p.N0 = g.N0; p.N1 = g.N1; p.R = g.R; p.RCH = g.RCH;
   p.p_drop = p_drop; p.seed = seed; p.seed_dev = (const unsigned long long*)seed_dev;
   p.x3 = s2ag::umma::g_precision == 0 ? 1 : 0;
-  auto kfn = &tcn_block_fused_kernel;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(&tcn_block_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(&tcn_block_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       s2ag_set_error("s2ag_tcn_block_fused_fwd: shared memory attribute"); return S2AG_ERR_LAUNCH;
     }
     attr_set = true;
   }
-  const int grid = p.tiles < sms ? p.tiles : sms;
-  S2AG_LAUNCH(kfn, grid, s2ag::tcnf::THREADS, g.smem, stream, p);
+  if (pair) {
+    const int units = (p.tiles + 1) / 2, max_pairs = sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (units < max_pairs ? units : max_pairs));
+    cfg.blockDim = dim3(s2ag::tcnf::THREADS);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ++g_s2ag_launches;
+    if (cudaLaunchKernelEx(&cfg, &tcn_block_fused_kernel<true>, p) != cudaSuccess) {
+      s2ag_set_error("s2ag_tcn_block_fused_fwd: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return S2AG_ERR_LAUNCH;
+    }
+  } else {
+    auto kfn = &tcn_block_fused_kernel<false>;
+    const int grid = p.tiles < sms ? p.tiles : sms;
+    S2AG_LAUNCH(kfn, grid, s2ag::tcnf::THREADS, g.smem, stream, p);
+  }
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }

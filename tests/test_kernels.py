@@ -461,7 +461,8 @@ def test_no_reference_cycles(dev):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,T,C,d,p", [(7, 34, 300, 1, 0.0), (7, 34, 300, 8, 0.3), (2, 100, 300, 8, 0.3), (5, 34, 24, 4, 0.2),
                                         (150, 34, 300, 2, 0.3)])
-def test_tcn_block_fused_vs_two_launch(B, T, C, d, p):
+@pytest.mark.parametrize("pair", [False, True])
+def test_tcn_block_fused_vs_two_launch(B, T, C, d, p, pair):
     """single-kernel TCN block (csrc/umma_tcn.cu) against the two conv-as-GEMM launches (csrc/tcn.cu) from the same
     dropout seed (identical masks): output, saved activations through the backward pass, all parameter gradients.
     Covers the column split of the accumulator (C = 300 -> 160 + 144), partial last tiles, one clip per tile."""
@@ -476,6 +477,7 @@ def test_tcn_block_fused_vs_two_launch(B, T, C, d, p):
     g = torch.randn(B, T, C)
     res = {}
     default = ops.TCN_FUSED[0]
+    _C.lib().s2ag_debug_flags(8192 if pair else 0)   # CTA-pair (cta_group::2) variant of the fused kernel
     for fused in (True, False):
         ops.TCN_FUSED[0] = fused
         try:
@@ -508,4 +510,5 @@ def test_tcn_block_fused_vs_two_launch(B, T, C, d, p):
             y0 = ops.tcn_block(x.to(dev), *ps, d, p, training=True)
     finally:
         ops.TCN_FUSED[0] = default
+    _C.lib().s2ag_debug_flags(0)
     close(y0, res[True][0], what="no-grad out")
