@@ -176,7 +176,6 @@ def roofline(B, dev, lib, clips_per_s_per_gpu=None):
     bf16 burst peak although they run fp32-grade bf16x3 (3 MMAs per algorithmic MAC: ceiling 1/3 of that peak)."""
     import torch
     from speech2affective_gestures_b200 import _C, ops
-    from speech2affective_gestures_b200.net.tcn import TemporalBlock
     from speech2affective_gestures_b200.net.multimodal_context_net_v2 import WavEncoder
     pk = peaks()
     T, H = 34, 300
@@ -224,14 +223,36 @@ def roofline(B, dev, lib, clips_per_s_per_gpu=None):
                                            K, 0, 0.0, st), flush)
     entry("gemm_gru_projection", "pack_operand_kernel + gemm_umma_pk_kernel (tcgen05; %dx%dx%d)" % (M, N, K), "tensor",
           ms, 2.0 * M * N * K, (M * K + N * K + M * N) * 4)
-    # (3) one causal-TCN residual block forward (weight-norm + 2 dilated convs + ReLU/residual), C=300, k=2
-    C = 300
-    tb = TemporalBlock(C, C, 2, 1, 2, 2, dropout=0.0).to(dev)
+    # (3) one causal-TCN residual block forward (weight-norm + 2 dilated convs + ReLU/residual), C=300, k=2, d=2, through
+    #     the C ABI with preallocated buffers: (a) the default two-launch path, (b) the single-kernel block
+    import ctypes
+    C, dil = 300, 2
     xt = torch.randn(B, T, C, device=dev)
-    with torch.no_grad():
-        ms = _time_call(torch, lambda: tb.forward_cl(xt), flush)
-    entry("tcn_residual_block_fwd", "weight_norm_fwd x2 + gemm_umma_pk_kernel<LdConv,EpiTcn> x2 (d=2)", "tensor", ms,
-          24.48e6 * B, 81600.0 * B)
+    v1, v2 = torch.randn(C, C, 2, device=dev) * 0.05, torch.randn(C, C, 2, device=dev) * 0.05
+    g1, g2 = torch.ones(C, device=dev), torch.ones(C, device=dev)
+    b1, b2 = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    w1, w2 = torch.empty(C, 2, C, device=dev), torch.empty(C, 2, C, device=dev)
+    n1, n2 = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    y1, y2, yo = (torch.empty(B, T, C, device=dev) for _ in range(3))
+    P_ = ops._p
+
+    def tcn_two_launch():
+        _C.call("s2ag_weight_norm_fwd", P_(v1), P_(g1), P_(w1), P_(n1), C, C, 2, st)
+        _C.call("s2ag_weight_norm_fwd", P_(v2), P_(g2), P_(w2), P_(n2), C, C, 2, st)
+        _C.call("s2ag_tcn_block_fwd", P_(xt), P_(w1), P_(b1), P_(w2), P_(b2), P_(y1), P_(y2), P_(yo), B, T, C, dil, 0.0,
+                ctypes.c_uint64(0), None, st)
+    ms = _time_call(torch, tcn_two_launch, flush)
+    entry("tcn_residual_block_fwd", "weight_norm_fwd x2 + pack_operand x2 + gemm_umma_pk_kernel<LdConv,EpiTcn> x2 (d=2; the "
+          "default path)", "tensor", ms, 24.48e6 * B, 81600.0 * B)
+    n_ws = lib.s2ag_tcn_fused_ws_floats(T, C, dil)
+    if n_ws > 0:
+        wsf = torch.empty(n_ws, device=dev)
+        ms = _time_call(torch, lambda: _C.call(
+            "s2ag_tcn_block_fused_fwd", P_(xt), P_(v1), P_(g1), P_(b1), P_(v2), P_(g2), P_(b2), P_(w1), P_(w2), P_(n1),
+            P_(n2), None, None, P_(yo), P_(wsf), B, T, C, dil, 0.0, ctypes.c_uint64(0), None, st), flush)
+        entry("tcn_residual_block_fused_fwd", "tcn_pack_kernel + tcn_block_fused_kernel (umma_tcn.cu: one kernel per block, "
+              "y1 kept in shared memory; opt-in, bound by the weight stream: DESIGN.md)", "tensor", ms, 24.48e6 * B,
+              81600.0 * B)
     # (4) the frozen baseline's WavEncoder stack (4 strided Conv1d + 3 train-mode BN + LeakyReLU), raw audio in
     we = WavEncoder().to(dev)
     audio = torch.rand(B, AUDIO_LEN, device=dev) - 0.5

@@ -55,6 +55,23 @@ void s2ag_set_error(const char* fmt, ...);
 
 static inline int s2ag_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+#ifndef S2AG_EMU
+// SMs of the current device (queried once; 148 on B200): the residency bound of the persistent kernels and the grid
+// multiple of the grid-stride ones
+static inline int s2ag_sm_count() {
+  static int sms = 0;
+  if (sms <= 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+#else
+static inline int s2ag_sm_count() { return 148; }
+#endif
+
 // activation codes shared by every epilogue (mirrors the reference's nn.LeakyReLU slopes,
 // SURVEY Appendix B): 0 none, 1 ReLU, 2 LeakyReLU(slope)
 #define S2AG_ACT_NONE 0

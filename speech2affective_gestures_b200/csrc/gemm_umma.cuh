@@ -383,7 +383,7 @@ static inline void launch(const LdA& a, const LdB& b, const Epi& epi, int M, int
   const int BN = pick_bn(N);
   const int tiles = s2ag_cdiv(N, BN) * s2ag_cdiv(M, BM) * nbatch;
   if (splitk > 1) {
-    int sk = 148 / tiles;
+    int sk = s2ag_sm_count() / tiles;
     const int maxk = K / (4 * BK);
     if (sk > maxk) sk = maxk;
     if (sk < 1) sk = 1;

@@ -277,7 +277,7 @@ bool conv_shift_launch(const float* x, long ldpix_x, int N, int H, int W, int Ci
   size_t smem_req = smem;
   const size_t min_req = (size_t)(225 * 1024) / (per_sm + 1) + 2048;
   if (smem_req < min_req) smem_req = min_req;
-  int grid = 148 * per_sm;
+  int grid = s2ag_sm_count() * per_sm;
   if (grid > p.tiles) grid = p.tiles;
   S2AG_LAUNCH(kfn, grid, CTHREADS, smem_req, stream, p);
   return true;

@@ -715,7 +715,7 @@ bool gru_persist_supported(int H) {
 }
 static int gru_persist_tiles_per_launch(int H) {
   const int S = grup::kpad_of(H) / grup::HS;
-  int tiles = 148 / (2 * S);
+  int tiles = s2ag_sm_count() / (2 * S);   // every CTA of a launch must be resident (inter-CTA flags)
   return tiles < 1 ? 0 : tiles;
 }
 // bytes of exchange workspace (operand images + counters) for a batch of B clips

@@ -546,11 +546,7 @@ extern "C" int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const f
     auto kp = &tcn_pack_kernel;
     S2AG_LAUNCH(kp, dim3(g.Cpad, 2), 128, 0, stream, v1, g1, v2, g2, w1, w2, n1, n2, wpk, C, g.Cpad, g.KS, g.N0, pair ? 1 : 0);
   }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = s2ag_sm_count();
   Params p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.wpk = wpk; p.y1 = y1; p.y2 = y2; p.out = out;
   p.B = B; p.T = T; p.C = C; p.d = dilation; p.G = g.G; p.pitch = g.pitch; p.tiles = tiles;

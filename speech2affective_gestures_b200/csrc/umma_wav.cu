@@ -634,11 +634,7 @@ extern "C" int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float
   S2AG_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 31) == 0);
   S2AG_CHECK_ARG(slope >= 0.f && slope <= 1.f);   // LeakyReLU evaluated as max(v, slope * v)
   cudaStream_t st = (cudaStream_t)stream;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = s2ag_sm_count();
   // workspace: raw conv2 output, raw conv3 output, sums (doubles) of conv1 / conv2 / conv3, packed weight images
   float* y2 = ws;
   float* y3 = y2 + (long)B * L2 * 32;

@@ -322,7 +322,7 @@ bool conv_wgrad_shift_launch(const float* dy, long ldpix_dy, const float* x, lon
   if (per_sm == 1 && smem_req < (size_t)116 * 1024) smem_req = (size_t)116 * 1024;
   if (per_sm == 2 && smem_req < (size_t)78 * 1024) smem_req = (size_t)78 * 1024;   // never three
   int grid = p.tiles;
-  if (grid > 148 * per_sm) grid = 148 * per_sm;
+  if (grid > s2ag_sm_count() * per_sm) grid = s2ag_sm_count() * per_sm;
   if (grid < 1) grid = 1;
   S2AG_LAUNCH(kfn, grid, WTHREADS, smem_req, stream, p);
   return true;
