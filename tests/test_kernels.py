@@ -512,3 +512,31 @@ def test_tcn_block_fused_vs_two_launch(B, T, C, d, p, pair):
         ops.TCN_FUSED[0] = default
     _C.lib().s2ag_debug_flags(0)
     close(y0, res[True][0], what="no-grad out")
+
+
+@pytest.mark.gpu
+def test_tcn_block_fused_bf16x1_mode():
+    """single-pass bf16 operands (s2ag_set_precision(1)) through the single-kernel TCN block: hi-plane-only path"""
+    dev = torch.device("cuda:0")
+    from speech2affective_gestures_b200 import _C
+    if _C.is_emulated():
+        _C._lib, _C._emulated = None, False
+    torch.manual_seed(3)
+    B, T, C, d = 7, 34, 300, 4
+    raw = [torch.randn(C, C, 2) * 0.08, torch.rand(C, 1, 1) + 0.5, torch.randn(C) * 0.1,
+           torch.randn(C, C, 2) * 0.08, torch.rand(C, 1, 1) + 0.5, torch.randn(C) * 0.1]
+    ps = [t.to(dev) for t in raw]
+    x = torch.randn(B, T, C, device=dev)
+    default = ops.TCN_FUSED[0]
+    out = {}
+    try:
+        ops.TCN_FUSED[0] = True
+        with torch.no_grad():
+            out[0] = ops.tcn_block(x, *ps, d, 0.0, training=False)
+            assert _C.lib().s2ag_set_precision(1) == 0
+            out[1] = ops.tcn_block(x, *ps, d, 0.0, training=False)
+    finally:
+        _C.lib().s2ag_set_precision(0)
+        ops.TCN_FUSED[0] = default
+    err = (out[1] - out[0]).abs().max().item() / out[0].abs().max().item()
+    assert 1e-6 < err < 3e-2

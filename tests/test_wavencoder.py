@@ -82,3 +82,20 @@ def test_wavencoder_large_batch_property():
         b = we(audio[perm].contiguous())
     assert torch.isfinite(a).all()
     assert rel(b, a[perm]) < 2e-5
+
+
+def test_wavencoder_fused_bf16x1_mode():
+    """BASELINE config 3's single-pass bf16 operand mode (s2ag_set_precision(1)): the hi-plane-only code path of the
+    fused kernels; a throughput mode, bounded here at 3e-2 like the contraction engine's bf16x1 test"""
+    from speech2affective_gestures_b200 import _C
+    ref, we = _pair(5)
+    ref.train(); we.train()
+    audio = torch.rand(3, 36267, dtype=torch.float64) - 0.5
+    with torch.no_grad():
+        want = ref(audio.unsqueeze(1)).transpose(1, 2)
+        assert _C.lib().s2ag_set_precision(1) == 0
+        try:
+            got = we(audio.float().cuda())
+        finally:
+            _C.lib().s2ag_set_precision(0)
+    assert 1e-5 < rel(got, want) < 3e-2
