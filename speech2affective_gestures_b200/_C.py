@@ -79,8 +79,11 @@ def lib():
 
 
 def _inject_for_tests(path, strict=True):
-    """tests/emu only: route calls to the CPU kernel-logic emulator build."""
+    """tests/emu only: route calls to the CPU kernel-logic emulator build.  Refused unless the test harness says so
+    (S2AG_ALLOW_EMU=1, set by tests/conftest.py): the product path never runs on the emulator."""
     global _lib, _emulated
+    if os.environ.get("S2AG_ALLOW_EMU") != "1":
+        raise S2agError("the kernel-logic emulator is test infrastructure (set S2AG_ALLOW_EMU=1 in the test harness)")
     _lib = _bind(ctypes.CDLL(path), strict)
     _emulated = _lib.s2ag_is_device_build() == 0
     return _lib

@@ -710,13 +710,38 @@ int gru_debug_read_timeline(long long* host, int n) {
 }
 
 // A launch keeps every CTA resident: at most 148 CTAs -> batch chunks of `rows_per_launch` clips.
+static size_t bwd_smem_bytes(int H);
+static bool gru_persist_resident(int H);
 bool gru_persist_supported(int H) {
-  return H >= 16 && grup::persist_smem_bytes(H) <= 227 * 1024 && grup::kpad_of(H) / grup::HS <= grup::MAX_SLICES;
+  return H >= 16 && grup::persist_smem_bytes(H) <= 227 * 1024 && grup::kpad_of(H) / grup::HS <= grup::MAX_SLICES &&
+         gru_persist_resident(H);
 }
 static int gru_persist_tiles_per_launch(int H) {
   const int S = grup::kpad_of(H) / grup::HS;
   int tiles = s2ag_sm_count() / (2 * S);   // every CTA of a launch must be resident (inter-CTA flags)
   return tiles < 1 ? 0 : tiles;
+}
+// Residency is verified, not assumed: the CTAs of a launch poll each other's flags, so all S x 2 x tiles CTAs of the
+// largest launch must fit on the device at once (occupancy x SMs); otherwise gru_persist_supported() is false and the
+// per-step kernels of gru.cu run.  Cached per hidden size.
+static bool gru_persist_resident(int H) {
+  static int cache[512];   // 0 unknown, 1 yes, 2 no
+  if (H < 0 || H >= 512) return false;
+  if (cache[H]) return cache[H] == 1;
+  using namespace grup;
+  const int S = kpad_of(H) / HS, tiles = gru_persist_tiles_per_launch(H);
+  bool ok = tiles > 0;
+  if (ok) {
+    cudaFuncSetAttribute(&gru_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(&gru_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int f = 0, b = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, &gru_persist_fwd_kernel, FWD_THREADS, persist_smem_bytes(H)) == cudaSuccess &&
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, &gru_persist_bwd_kernel, PTHREADS, bwd_smem_bytes(H)) == cudaSuccess &&
+         (long)f * s2ag_sm_count() >= (long)S * 2 * tiles && (long)b * s2ag_sm_count() >= (long)S * 2 * tiles;
+    if (!ok) cudaGetLastError();
+  }
+  cache[H] = ok ? 1 : 2;
+  return ok;
 }
 // bytes of exchange workspace (operand images + counters) for a batch of B clips
 size_t gru_persist_ws_bytes(int B, int H) {

@@ -582,9 +582,10 @@ def dropout(x, p, training):
 
 # ------------------------------------------------------------------------------------------ TCN residual block
 # Single-kernel TCN block (csrc/umma_tcn.cu) vs two conv-as-GEMM launches (csrc/tcn.cu).  Measured at 256 clips (B200):
-# 74 us + 7 us packing on 86 SMs against 2 x 34 us + 17 us weight_norm/packing on 136 SMs, and 13.80 vs 13.50 ms per GAN
-# step -- the fused kernel is bound by streaming the 1.5 MB weight image through every SM, so the two-launch
-# path stays the default; S2AG_TCN_FUSED=1 selects the fused kernel (parity-tested either way).
+# 72 us (2 launches, 86 SMs) against 77 us (6 launches, 136 SMs) timed alone, but 13.80 vs 13.50 ms per GAN step where the
+# block shares the device with the recurrent kernels -- the fused kernel is bound by streaming the 1.5 MB weight image
+# through every SM, so the two-launch path stays the default; S2AG_TCN_FUSED=1 selects the fused kernel
+# (parity-tested either way).
 TCN_FUSED = [os.environ.get("S2AG_TCN_FUSED", "0") == "1"]
 
 

@@ -4,6 +4,7 @@ import sys
 import pytest
 import torch
 
+os.environ.setdefault("S2AG_ALLOW_EMU", "1")   # the CPU logic-emulator build may be injected by this harness only
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
