@@ -20,8 +20,8 @@
 //     image of conv2 over the x image (and to HBM only when the backward pass needs it); conv2 accumulates into the
 //     same TMEM columns; its epilogue adds bias, ReLU, dropout, the residual x (re-read from L2) and the final ReLU --
 //     for column half 0 while the MMAs of half 1 are still running.
-// Roles: warps 0-15 stage x and run both epilogues (4 per TMEM lane quadrant, a quarter of the columns each), warp 16
-// issues the MMAs, warp 17 drives the TMA ring.
+// Roles: warps 0-15 stage x and run both epilogues (4 per TMEM lane quadrant, a quarter of the columns each), warps 16
+// and 17 issue the MMAs (alternate ring items), warp 18 drives the TMA ring.
 #include "s2ag.h"
 #include "gemm_umma.cuh"
 #include "gemm_umma_packed.cuh"
@@ -31,11 +31,12 @@ namespace tcnf {
 
 using namespace s2ag::umma;
 
-constexpr int TM = 128, NWW = 16, NWORK = NWW * 32, THREADS = NWORK + 64, HDR = 1024;   // 16 worker warps + issuer + TMA
-constexpr int NSTAGE_1 = 5, NSTAGE_2 = 8;    // weight-ring slots: single CTA (10 KB each) / CTA pair (5 KB each; one relay warp per slot)
+constexpr int NISSUE = 3;              // MMA issuer threads of the single-CTA kernel (one warp each)
+constexpr int TM = 128, NWW = 16, NWORK = NWW * 32, THREADS = NWORK + 32 * (NISSUE + 1), HDR = 1024;   // 16 worker warps + issuers + TMA
+constexpr int NSTAGE_MAX = 12, NSTAGE_2 = 8;   // weight-ring slots: single CTA: as many 10 KB slots as fit (5..12) / CTA pair: 5 KB each, one relay warp per slot
 // mbarriers (8 bytes each): weights landed (own copy) | ring slot free | weights landed in the peer CTA (pair leader only) |
 // accumulator column half complete | operand image staged
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 128, BAR_PFULL = 256, BAR_ACC = 384, BAR_AREADY = 400, TMEM_SLOT = 416;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 128, BAR_PFULL = 256, BAR_ACC = 384, BAR_AREADY = 400, BAR_ORD = 408, TMEM_SLOT = 416;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
@@ -49,6 +50,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// long waits of many warps (the 16 worker warps while a convolution's MMAs run): poll with a sleep in between, so that
+// the polling does not compete with the tensor core's operand reads for the shared-memory pipe
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if (++spins > (1u << 22)) __trap();
+  }
 }
 // CTA-pair forms (semantics checked by tools/mma2_probe.cu): M = 256 over the pair, each CTA supplies its 128 rows of A and
 // its half of B's rows from the SAME shared-memory offsets; the commit arrives on the barrier at that offset in both CTAs
@@ -69,7 +79,8 @@ struct Params {
   const unsigned char* wpk;     // [conv][column half h][k-step = tap * KS + s][plane hi|lo][2 chunks][N_h][16 B]
   float* y1; float* y2; float* out;   // y1 / y2 may be NULL (no backward pass)
   int B, T, C, d, G, pitch, tiles;
-  int Kc, Cpad, KS, N0, N1, R, RCH; // chunks of 8 channels, padded channels, k-steps per tap, MMA column split, rows
+  int Kc, Cpad, KS, N0, N1, Rv, RCH, nstage; // chunks of 8 channels, padded channels, k-steps per tap, MMA column split,
+                                             // anchor rows that can be valid (G * pitch), image rows per chunk, ring slots
   float p_drop; unsigned long long seed; const unsigned long long* seed_dev;
   int x3;
 };
@@ -166,7 +177,7 @@ __device__ long long g_tcn_tl[3][16];   // [worker | issuer | producer][mark]: c
 
 template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
-  constexpr int NSTAGE = PAIR ? NSTAGE_2 : NSTAGE_1;
+  const int NSTAGE = PAIR ? NSTAGE_2 : p.nstage;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // PAIR: 2-CTA cluster, rank 0 issues the MMAs for both
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -185,8 +196,9 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(sbase + BAR_WFULL + 8 * s, 1); mbar_init(sbase + BAR_WEMPTY + 8 * s, 1); mbar_init(sbase + BAR_PFULL + 8 * s, 1);
     }
-    mbar_init(sbase + BAR_ACC, 1);
-    mbar_init(sbase + BAR_ACC + 8, 1);
+    mbar_init(sbase + BAR_ACC, PAIR ? 1 : NISSUE);    // single-CTA kernel: every issuer thread commits
+    mbar_init(sbase + BAR_ACC + 8, PAIR ? 1 : NISSUE);
+    mbar_init(sbase + BAR_ORD, 1);
     mbar_init(sbase + BAR_AREADY, PAIR ? 2 * NWW : NWW);   // PAIR: the leader's barrier also collects the peer's workers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -235,12 +247,14 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       // ---- x -> operand image (item = (row, chunk), chunk fastest: coalesced 32-byte reads; RCH odd: conflict-free)
       const bool vec_x = (p.C & 3) == 0;
       if (warp == 0) TCN_MARK(0, 0);
-      for (int base = 0; base < TM * p.Kc; base += 4 * NWORK) {
+      // only the G * pitch rows that can hold a clip (or its padding) are staged: the image is truncated there, the MMA
+      // reads its 128 rows past the end into whatever follows (garbage rows of the accumulator, never stored)
+      for (int base = 0; base < p.Rv * p.Kc; base += 4 * NWORK) {
         float4 va[4], vb[4]; int dst[4]; bool ok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int it = base + tid + NWORK * i;
-          ok[i] = it < TM * p.Kc;
+          ok[i] = it < p.Rv * p.Kc;
           const int kc = it % p.Kc, r = it / p.Kc;
           const int g = r / p.pitch, tt = r - g * p.pitch;
           dst[i] = (kc * p.RCH + LEAD + r) * 16;
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       // ---- epilogue 1: y1 = drop(relu(acc + b1)) -> operand image of conv2 (zeros in the padding rows)
       if (warp == 0) TCN_MARK(0, 1);
       relay(0);
-      mbar_wait(acc_bar1, 0u);
+      mbar_wait_sleep(acc_bar1, 0u);
       if (warp == 0) TCN_MARK(0, 2);
       tc_fence_after();
       for (int ch = ch_beg; ch < ch_end; ++ch) {
@@ -329,11 +343,13 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
               if (ch * 8 + e < p.C) p.y1[grow + ch * 8 + e] = v[e];
           }
         }
-        uint4 hi, lo;
-        pack8t(v, hi, lo);
-        const int dst = (ch * p.RCH + LEAD + row) * 16;
-        *reinterpret_cast<uint4*>(a_hi + dst) = hi;
-        if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst) = lo;
+        if (row < p.Rv) {
+          uint4 hi, lo;
+          pack8t(v, hi, lo);
+          const int dst = (ch * p.RCH + LEAD + row) * 16;
+          *reinterpret_cast<uint4*>(a_hi + dst) = hi;
+          if (p.x3) *reinterpret_cast<uint4*>(a_lo + dst) = lo;
+        }
       }
       tc_fence_before();
       fence_async_smem();
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       // ---- epilogue 2: y2 = drop(relu(acc + b2)); out = relu(y2 + x)
       if (warp == 0) TCN_MARK(0, 3);
       relay(1);
-      mbar_wait(acc_bar2, 1u);
+      mbar_wait_sleep(acc_bar2, 1u);
       if (warp == 0) TCN_MARK(0, 4);
       tc_fence_after();
       auto load_res = [&](int ch, float4& ra, float4& rb) {
@@ -398,18 +414,28 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
       // the image and the accumulator are reused by the next tile: all epilogue warps must be done reading
       asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
     }
-  } else if (warp_u == NWW) {
-    // ====================================================================================================== issuer
-    if (elect_one()) {
+  } else if (warp_u >= NWW && warp_u < NWW + NISSUE) {
+    // ===================================================================================================== issuers
+    // Single-CTA kernel: TWO issuer threads take the ring items alternately.  Measured (tools/tcn_timeline.cu): one thread
+    // needs ~470 cycles per item -- a tcgen05.mma issue blocks until the pipe accepts it (~73 cycles each at N = 160) and
+    // the mbarrier wait for the next item (~180 cycles) starts only after the third issue -- against 220 cycles of MMA
+    // time; with two threads one thread's wait overlaps the other's issues.  Both accumulate into the same TMEM
+    // columns: the thread that owns the first k-step of a column half (accumulate = 0) releases the other through the
+    // ORD barrier once that MMA is issued (the pipe executes in issue order).  PAIR: one issuer (the cluster leader).
+    const int iss = warp_u - NWW;
+    constexpr int NISS = PAIR ? 1 : NISSUE;
+    if (iss < NISS && elect_one()) {
       if (!PAIR || rank == 0) {
         const uint32_t idesc0 = PAIR ? make_idesc_pair(p.N0) : make_idesc(p.N0);
         const uint32_t idesc1 = PAIR ? make_idesc_pair(p.N1 > 0 ? p.N1 : 16) : make_idesc(p.N1 > 0 ? p.N1 : 16);
-        uint32_t n = 0, aphase = 0;
+        uint32_t aphase = 0, ophase = 0;
+        uint32_t n = 0;                                // global ring item counter (both issuers count all items)
+        int stage = 0; uint32_t sphase = 0;            // ring slot / phase parity of item n, advanced incrementally
         for (int tl = 0; tl < my_tiles; ++tl) {
           for (int conv = 0; conv < 2; ++conv) {
-            TCN_MARK(1, conv * 4);
+            if (iss == 0) TCN_MARK(1, conv * 4);
             mbar_wait(sbase + BAR_AREADY, aphase); aphase ^= 1u;
-            TCN_MARK(1, conv * 4 + 1);
+            if (iss == 0) TCN_MARK(1, conv * 4 + 1);
             tc_fence_after();
             for (int hN = 0; hN < 2; ++hN) {
               const int Nh = hN ? p.N1 : p.N0;
@@ -418,41 +444,48 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
                 const uint32_t d = tmem_base + (hN ? (uint32_t)p.N0 : 0u);
                 const uint32_t idesc = hN ? idesc1 : idesc0;
                 const uint32_t plane = (uint32_t)(2 * Nl * 16);
+                const bool first_mine = (int)(n % (uint32_t)NISS) == iss;      // who issues k-step 0 of this half
+                if (NISS > 1 && !first_mine) { mbar_wait(sbase + BAR_ORD, ophase); }
                 for (int ks = 0; ks < n_steps; ++ks, ++n) {
-                  const int stage = n % NSTAGE;
-                  mbar_wait(sbase + BAR_WFULL + 8 * stage, (n / NSTAGE) & 1);
-                  if (PAIR) mbar_wait(sbase + BAR_PFULL + 8 * stage, (n / NSTAGE) & 1);   // the peer's share has landed too
-                  tc_fence_after();
-                  const int j = ks / p.KS, s = ks - j * p.KS;           // tap (0: t - d, 1: t), 16-channel group
-                  const uint32_t ah = smem_u32(a_hi) + (uint32_t)((2 * s * p.RCH + LEAD - (j == 0 ? p.d : 0)) * 16);
-                  const uint32_t al = ah + (uint32_t)a_plane;
-                  const uint32_t wh = smem_u32(wst) + (uint32_t)(stage * stage_slot), wl = wh + plane;
-                  const uint64_t dah = make_desc(ah, p.RCH * 16, 128), dwh = make_desc(wh, Nl * 16, 128);
-                  const uint64_t dal = make_desc(al, p.RCH * 16, 128), dwl = make_desc(wl, Nl * 16, 128);
-                  if (PAIR) {
-                    if (p.x3) {
-                      mma_bf16_pair(d, dal, dwh, idesc, ks ? 1u : 0u);
-                      mma_bf16_pair(d, dah, dwl, idesc, 1u);
-                      mma_bf16_pair(d, dah, dwh, idesc, 1u);
+                  if ((int)(n % (uint32_t)NISS) == iss) {
+                    mbar_wait(sbase + BAR_WFULL + 8 * stage, sphase);
+                    if (PAIR) mbar_wait(sbase + BAR_PFULL + 8 * stage, sphase);   // the peer's share has landed too
+                    tc_fence_after();
+                    const int j = ks / p.KS, s = ks - j * p.KS;           // tap (0: t - d, 1: t), 16-channel group
+                    const uint32_t ah = smem_u32(a_hi) + (uint32_t)((2 * s * p.RCH + LEAD - (j == 0 ? p.d : 0)) * 16);
+                    const uint32_t al = ah + (uint32_t)a_plane;
+                    const uint32_t wh = smem_u32(wst) + (uint32_t)(stage * stage_slot), wl = wh + plane;
+                    const uint64_t dah = make_desc(ah, p.RCH * 16, 128), dwh = make_desc(wh, Nl * 16, 128);
+                    const uint64_t dal = make_desc(al, p.RCH * 16, 128), dwl = make_desc(wl, Nl * 16, 128);
+                    if (PAIR) {
+                      if (p.x3) {
+                        mma_bf16_pair(d, dal, dwh, idesc, ks ? 1u : 0u);
+                        mma_bf16_pair(d, dah, dwl, idesc, 1u);
+                        mma_bf16_pair(d, dah, dwh, idesc, 1u);
+                      } else {
+                        mma_bf16_pair(d, dah, dwh, idesc, ks ? 1u : 0u);
+                      }
+                      mma_commit_pair(sbase + BAR_WEMPTY + 8 * stage);
                     } else {
-                      mma_bf16_pair(d, dah, dwh, idesc, ks ? 1u : 0u);
+                      if (p.x3) {
+                        mma_bf16(d, dal, dwh, idesc, ks ? 1u : 0u);
+                        if (NISS > 1 && ks == 0) mbar_arrive_cta(sbase + BAR_ORD);   // the accumulator is initialised in issue order
+                        mma_bf16(d, dah, dwl, idesc, 1u);
+                        mma_bf16(d, dah, dwh, idesc, 1u);
+                      } else {
+                        mma_bf16(d, dah, dwh, idesc, ks ? 1u : 0u);
+                        if (NISS > 1 && ks == 0) mbar_arrive_cta(sbase + BAR_ORD);
+                      }
+                      mma_commit(sbase + BAR_WEMPTY + 8 * stage);
                     }
-                    mma_commit_pair(sbase + BAR_WEMPTY + 8 * stage);
-                  } else {
-                    if (p.x3) {
-                      mma_bf16(d, dal, dwh, idesc, ks ? 1u : 0u);
-                      mma_bf16(d, dah, dwl, idesc, 1u);
-                      mma_bf16(d, dah, dwh, idesc, 1u);
-                    } else {
-                      mma_bf16(d, dah, dwh, idesc, ks ? 1u : 0u);
-                    }
-                    mma_commit(sbase + BAR_WEMPTY + 8 * stage);
                   }
+                  if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                 }
+                ophase ^= 1u;
               }
-              // this column half of the accumulator is complete (in both CTAs of a pair)
+              // this column half of the accumulator is complete (in both CTAs of a pair) once every issuer's MMAs are
               if (PAIR) mma_commit_pair(sbase + BAR_ACC + 8 * hN); else mma_commit(sbase + BAR_ACC + 8 * hN);
-              TCN_MARK(1, conv * 4 + 2 + hN);
+              if (iss == 0) TCN_MARK(1, conv * 4 + 2 + hN);
             }
           }
         }
@@ -462,7 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
     // ================================================================================================ TMA producer
     if (elect_one()) {
       const long conv_bytes = (long)n_steps * (2L * 2 * p.Cpad * 16);
-      uint32_t n = 0;
+      int stage = 0; uint32_t ephase = 1; bool first_round = true;   // parity of the "slot free" phase to wait for
       for (int tl = 0; tl < my_tiles; ++tl) {
         for (int conv = 0; conv < 2; ++conv) {
           for (int hN = 0; hN < 2; ++hN) {
@@ -472,9 +505,8 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
             const uint32_t mine = PAIR ? sb / 2 : sb;                 // this CTA's share (PAIR: its half of the B rows)
             const unsigned char* base = p.wpk + conv * conv_bytes + (hN ? (long)n_steps * (2L * 2 * p.N0 * 16) : 0) +
                                         (PAIR ? (long)rank * mine : 0);
-            for (int ks = 0; ks < n_steps; ++ks, ++n) {
-              const int stage = n % NSTAGE;
-              if (n >= NSTAGE) mbar_wait(sbase + BAR_WEMPTY + 8 * stage, ((n / NSTAGE) - 1) & 1);
+            for (int ks = 0; ks < n_steps; ++ks) {
+              if (!first_round) mbar_wait(sbase + BAR_WEMPTY + 8 * stage, ephase);
               const unsigned char* src = base + (long)ks * sb;
               const uint32_t dst = smem_u32(wst) + (uint32_t)(stage * stage_slot);
               const uint32_t bar = sbase + BAR_WFULL + 8 * stage;
@@ -482,6 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
               // (measured: two 5 KB copies per item 500 cycles, two 2.5 KB copies 640, one 19.5 KB copy 680)
               mbar_expect_tx(bar, mine);
               bulk_g2s(dst, src, mine, bar);
+              if (++stage == NSTAGE) { stage = 0; ephase ^= 1u; first_round = false; }
             }
           }
         }
@@ -500,17 +533,25 @@ __global__ void __launch_bounds__(THREADS, 1) tcn_block_fused_kernel(Params p) {
 
 static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 
-struct Geom { int Kc, Cpad, KS, N0, N1, G, pitch, R, RCH; size_t smem; long wpk_bytes; bool ok; };
+int g_nstage_cap = 0;   // measurement aid (tools/tcn_timeline.cu): upper bound on the ring slots, 0 = as many as fit
+struct Geom { int Kc, Cpad, KS, N0, N1, G, pitch, Rv, RCH, nstage; size_t smem; long wpk_bytes; bool ok; };
 static Geom geom(int T, int C, int d) {
   Geom g;
   g.Cpad = rup(C, 16); g.Kc = g.Cpad / 8; g.KS = g.Cpad / 16;
   g.N0 = g.Cpad <= 256 ? g.Cpad : rup(g.Cpad / 2, 16);
   g.N1 = g.Cpad - g.N0;
   g.pitch = T + d; g.G = g.pitch <= TM ? TM / g.pitch : 0;
-  g.R = TM + d; g.RCH = g.R | 1;
-  g.smem = HDR + 2 * (size_t)g.Cpad * 4 + 2 * (size_t)g.Kc * g.RCH * 16 + (size_t)NSTAGE_1 * 2 * 2 * g.N0 * 16;
+  g.Rv = g_nstage_cap < 0 ? TM : g.G * g.pitch; g.RCH = (g.Rv + d) | 1;          // image rows: d leading zero rows + the rows that can be valid
+  const size_t fixed = HDR + 2 * (size_t)g.Cpad * 4 + 2 * (size_t)g.Kc * g.RCH * 16, slot = (size_t)2 * 2 * g.N0 * 16;
+  // the MMA reads 128 rows from (at most) row d of the last chunk: the ring behind the image must cover that overhang
+  const size_t overhang = g.RCH < TM + d ? (size_t)(TM + d - g.RCH) * 16 : 0;
+  long ns = fixed < (size_t)227 * 1024 ? (long)(((size_t)227 * 1024 - fixed) / slot) : 0;
+  if (ns > NSTAGE_MAX) ns = NSTAGE_MAX;
+  if (g_nstage_cap > 0 && ns > g_nstage_cap) ns = g_nstage_cap;
+  g.nstage = (int)ns;
+  g.smem = fixed + (size_t)g.nstage * slot;
   g.wpk_bytes = 2L * 2 * g.KS * (2L * 2 * g.Cpad * 16);
-  g.ok = g.G >= 1 && g.Cpad <= 512 && g.N1 <= 256 && g.smem <= 227 * 1024 && C <= 320 && d >= 1;
+  g.ok = g.G >= 1 && g.Cpad <= 512 && g.N1 <= 256 && g.nstage >= 3 && (size_t)g.nstage * slot >= overhang && C <= 320 && d >= 1;
   return g;
 }
 
@@ -550,7 +591,7 @@ extern "C" int s2ag_tcn_block_fused_fwd(const float* x, const float* v1, const f
   Params p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.wpk = wpk; p.y1 = y1; p.y2 = y2; p.out = out;
   p.B = B; p.T = T; p.C = C; p.d = dilation; p.G = g.G; p.pitch = g.pitch; p.tiles = tiles;
-  p.Kc = g.Kc; p.Cpad = g.Cpad; p.KS = g.KS; p.N0 = g.N0; p.N1 = g.N1; p.R = g.R; p.RCH = g.RCH;
+  p.Kc = g.Kc; p.Cpad = g.Cpad; p.KS = g.KS; p.N0 = g.N0; p.N1 = g.N1; p.Rv = g.Rv; p.RCH = g.RCH; p.nstage = g.nstage;
   p.p_drop = p_drop; p.seed = seed; p.seed_dev = (const unsigned long long*)seed_dev;
   p.x3 = s2ag::umma::g_precision == 0 ? 1 : 0;
   static bool attr_set = false;
