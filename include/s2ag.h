@@ -57,7 +57,9 @@ int s2ag_set_precision(int mode);
  *   1024 L2-exchange GRU forward (umma_gru.cu) also where the cluster kernel (umma_gru_cluster.cu) is the default
  *   2048 cluster GRU forward for every supported hidden size (default: H <= 80; see umma_gru_cluster.cu)
  *   4096 cluster GRU forward: wait for every h slice before the first tcgen05.mma of a step (measurement)
- *   8192 fused TCN block: CTA-pair variant (tcgen05 cta_group::2, M = 256; measured slower than one CTA per tile) */
+ *   8192 fused TCN block: CTA-pair variant (tcgen05 cta_group::2, M = 256; measured slower than one CTA per tile)
+ *   16384 two-TMA contraction kernel (gemm_umma_tt.cuh: both operands pre-packed, 256-row tiles, three MMA issuers) for the
+ *         big weight-side contractions; measured on par with the packed-B kernel, hence opt-in */
 int s2ag_debug_flags(int flags);
 /* bring-up aid: clock64 timeline (64 steps x 16 marks) of one CTA of the last persistent GRU forward launched with
  * s2ag_debug_flags bit 1 set; copies n values to HOST memory (synchronises). */

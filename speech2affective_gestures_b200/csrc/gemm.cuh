@@ -7,6 +7,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
 #include "gemm_umma_packed.cuh"
+#include "gemm_umma_tt.cuh"
 
 namespace s2ag {
 extern int g_engine;  // 0 = auto, 1 = SIMT only
@@ -20,6 +21,9 @@ static inline void launch_gemm_untimed(const LdA& a, const LdB& b, const Epi& ep
     // B reused by >= 4 row tiles (a weight, or any operand small next to A): pack it once into the tensor-core
     // operand image and let the CTAs fetch it by TMA (gemm_umma_packed.cuh) -- needs a scratch buffer registered
     // for this stream (s2ag_register_scratch); without one the on-the-fly kernel runs.
+    // big weight-side contractions: both operands pre-packed, 256 x BN tiles, no conversion in the main loop
+    // (gemm_umma_tt.cuh); needs scratch for both operand images on this stream
+    if (!(umma::g_dbg_flags & 256) && umma::launch_tt(a, b, epi, M, N, K, nbatch, splitk, &scratch_get, stream)) return;
     if (M >= 4 * umma::BM && !(umma::g_dbg_flags & 256)) {
       const long bytes = umma::packed_bytes(N, K, nbatch);
       void* img = scratch_get(stream, bytes);

@@ -340,7 +340,32 @@ struct EpiGeneric {
     else if (mode == 1) *dst += v;
     else *dst = v;
   }
+  // Row-vector walk (a thread owns one output row and visits 8 consecutive columns at a time: two 16-byte stores, no
+  // transposition through shared memory): the common store / accumulate epilogues without column permutation or mask.
+  static constexpr bool kRowVec = true;
+  __device__ __forceinline__ bool row_vec_ok(bool partial) const {
+    return !partial && mode != 2 && perm_C == 0 && mul_src == nullptr && (ldc & 3) == 0 && (bstride & 3) == 0 &&
+           (reinterpret_cast<unsigned long long>(C) & 15ull) == 0;
+  }
+  __device__ __forceinline__ const float* bias_of(int b) const { return bias ? bias + b * bias_bstride : nullptr; }
+  // columns n .. n+7 (n % 4 == 0, all < N) of row m; bias8: this column group's bias values (zeros if there is no bias)
+  __device__ __forceinline__ void store_row8(int b, int m, int n, const float (&acc)[8], const float (&bias8)[8]) const {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = s2ag_act(fmaf(alpha, acc[i], bias8[i]), act, slope);
+    float4* dst = reinterpret_cast<float4*>(C + b * bstride + (long)m * ldc + n);
+    if (mode == 1) {
+      const float4 o0 = dst[0], o1 = dst[1];
+      v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+    }
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
 };
+// does an epilogue functor offer the row-vector path (store_row8) of the tcgen05 engines?
+template <class E, class = void> struct EpiHasRowVec { static constexpr bool value = false; };
+template <class E> struct EpiHasRowVec<E, decltype((void)E::kRowVec)> { static constexpr bool value = E::kRowVec; };
+
 static inline EpiGeneric make_epi(float* C, long ldc, const float* bias = nullptr, int act = 0, float slope = 0.f,
                                   int mode = 0) {
   EpiGeneric e; e.C = C; e.ldc = ldc; e.bstride = 0; e.bias = bias; e.bias_bstride = 0; e.alpha = 1.f;

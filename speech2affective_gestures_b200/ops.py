@@ -59,7 +59,7 @@ def _p(t):
 # Scratch for the packed weight-operand images of the tcgen05 contractions (s2ag_register_scratch): one buffer per
 # stream that launches library kernels, owned here.  Never allocated while a CUDA graph is being captured (a stream
 # first seen during capture simply runs the contractions that stage both operands on the fly).
-SCRATCH_BYTES = 64 << 20
+SCRATCH_BYTES = 192 << 20   # packed weight image + packed activation image of the largest contraction (gemm_umma_tt.cuh)
 _SCRATCH = {}
 
 

@@ -100,3 +100,44 @@ def test_persistent_gru_batch_chunking_matches_per_step_kernels():
     assert rel(y0, y1) < 2e-5 and rel(dx0, dx1) < 2e-4
     for a, b in zip(g0, g1):
         assert rel(a, b) < 5e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,act,accumulate", [(2176, 900, 600, 0, False), (1100, 300, 88, 2, False), (4352, 600, 1800, 0, True)])
+def test_two_tma_contraction_matches_packed_kernel(M, N, K, act, accumulate):
+    """gemm_umma_tt.cuh (both operands pre-packed and fetched by TMA, 256-row tiles, three MMA issuer threads; opt-in
+    through s2ag_debug_flags bit 16384) against the default packed-B kernel and fp64: linear forward (store epilogue,
+    ragged last row tile / column tile) and the accumulating data-gradient epilogue"""
+    import torch
+    from speech2affective_gestures_b200 import _C, ops
+    dev = torch.device("cuda:0")
+    if _C.is_emulated():
+        _C._lib, _C._emulated = None, False
+    torch.manual_seed(5)
+    x = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    b = torch.randn(N, device=dev)
+    st = ops._stream(x)
+    res = {}
+    for flag in (0, 16384):
+        _C.lib().s2ag_debug_flags(flag)
+        try:
+            if accumulate:   # dx[M,K'] += dy[M,N'] @ w[N',K']  with (N', K') = (K, N) of the forward naming
+                dx = torch.ones(M, N, device=dev)
+                _C.call("s2ag_linear_bwd_data", ops._p(x), K, ops._p(w.t().contiguous()), ops._p(dx), N, M, K, N, 1, st)
+                res[flag] = dx
+            else:
+                y = torch.empty(M, N, device=dev)
+                _C.call("s2ag_linear_fwd", ops._p(x), K, ops._p(w), ops._p(b), ops._p(y), N, M, N, K, act, 0.3, st)
+                res[flag] = y
+        finally:
+            _C.lib().s2ag_debug_flags(0)
+    if accumulate:
+        want = 1.0 + x.double() @ w.double().t()
+    else:
+        want = x.double() @ w.double().t() + b.double()
+        if act == 2:
+            want = torch.where(want > 0, want, 0.3 * want)
+    scale = want.abs().max().item()
+    assert (res[16384].double() - want).abs().max().item() <= 2e-5 * scale
+    assert (res[16384] - res[0]).abs().max().item() <= 2e-5 * scale
