@@ -320,6 +320,23 @@ int s2ag_dir_vec_to_pose(const float* vec, const float* mean, float* pose, long 
 int s2ag_pose_metrics(const float* out, const float* tgt, const float* mean, double* acc_ws, float* dst,
                       int B, int T, int n_pre, void* stream);
 
+/* ---- Frechet gesture distance on the device (net/embedding_space_evaluator.py) -----------
+ * Replaces the host lists of push_samples (:45-61) and the numpy / scipy get_scores (:73-101): a batch of paired latent
+ * features gen_feat / real_feat [N, D] (fp32, row pitches ld_*; D <= 32) is folded into the fp64 moment buffer `acc`
+ * (s2ag_fgd_acc_doubles(D) doubles, zeroed by the caller on reset): n, the paired L1 sum, per-dimension sums and the
+ * two D x D second-moment matrices. */
+long s2ag_fgd_acc_doubles(int D);
+int s2ag_fgd_accumulate(const float* gen_feat, long ld_gen, const float* real_feat, long ld_real, int N, int D,
+                        double* acc, void* stream);
+/* get_scores (:73-101): out2[0] = Frechet distance between N(mean, np.cov) of the generated and of the real features,
+ * out2[1] = mean per-sample L1 distance of the paired features ("feat_dist"). */
+int s2ag_fgd_scores(const double* acc, int D, double* out2, void* stream);
+/* calculate_frechet_distance (:104-152) for caller-given moments (fp64, device): out2[0] = |mu1 - mu2|^2 + Tr(sigma1)
+ * + Tr(sigma2) - 2 Tr(sqrtm(sigma1 sigma2)), the trace evaluated as the sum of the square roots of the eigenvalues of
+ * sigma1^(1/2) sigma2 sigma1^(1/2) (two fp64 Jacobi eigen-decompositions in one warp); out2[1] = 0. */
+int s2ag_frechet_distance(const double* mu1, const double* sigma1, const double* mu2, const double* sigma2, int D,
+                          double* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

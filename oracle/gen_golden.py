@@ -316,11 +316,65 @@ def checkpoints():
     print("wrote", ck, sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(ck) for f in fs), "bytes")
 
 
+def fgd():
+    """the UNMODIFIED reference EmbeddingSpaceEvaluator (net/embedding_space_evaluator.py) around a
+    reference-built EmbeddingNet(mode='pose') checkpoint in the reference's file schema ('embedding_dict'), fed three
+    batches of (generated, real) clips.  The fixture keeps the inputs, the reference's latent features,
+    reconstructions, recon_err_diff and get_scores(); the weights are oracle.fill_state_dict(seed) (portable)."""
+    import tempfile
+    import net.embedding_space_evaluator as rese
+    import fgd_oracle as FO
+    import inspect
+    from scipy import linalg as _sl
+    if 'disp' not in inspect.signature(_sl.sqrtm).parameters:
+        # harness shim for a third-party API change: scipy >= 1.18 dropped sqrtm's `disp` argument, which the reference
+        # passes (net/embedding_space_evaluator.py:138, written against scipy 1.x: disp=False -> (sqrtm, error estimate))
+        _sqrtm = _sl.sqrtm
+        rese.linalg = NS(sqrtm=lambda a, disp=True: (_sqrtm(a), 0.0) if disp is False else _sqrtm(a))
+    cfg = NS(**O.CFG)
+    lang = NS(n_words=N_WORDS, word_embedding_weights=None)
+    net = ren.EmbeddingNet(cfg, 27, cfg.n_poses, N_WORDS, cfg.wordembed_dim, None, 'pose')
+    sd = O.fill_state_dict(net.state_dict(), seed=777)
+    net.load_state_dict(sd)
+    n_batches, nb = 3, 24
+    real, gen = FO.synthetic_pairs(4321, n_batches, nb)
+    with tempfile.TemporaryDirectory() as base:
+        os.makedirs(os.path.join(base, 'outputs'))
+        torch.save({'embedding_dict': net.state_dict()}, os.path.join(base, 'outputs/embedding_net.pth.tar'))
+        ev = rese.EmbeddingSpaceEvaluator(base, cfg, 27, lang, torch.device('cpu'))
+    recon = []
+    for r, g in zip(real, gen):
+        rt, gt = torch.from_numpy(r), torch.from_numpy(g)
+        ev.push_samples(None, None, gt, rt)
+        with torch.no_grad():
+            recon.append(ev.net(None, None, rt[:, :cfg.n_pre_poses], gt, 'pose')[6].numpy())
+    fd, feat_dist = ev.get_scores()
+    gfeat, rfeat = np.vstack(ev.generated_feat_list), np.vstack(ev.real_feat_list)
+    # pin the restatement
+    sdo = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        o_feat = FO.pose_encoder(sdo, torch.from_numpy(np.concatenate(gen))).numpy()
+        o_rec = FO.pose_decoder(sdo, torch.from_numpy(o_feat)).numpy()
+    o_fd, o_fdist = FO.get_scores(gfeat, rfeat)
+    print("oracle vs reference: feat %.2e recon %.2e fgd %.2e feat_dist %.2e" % (
+        np.abs(o_feat - gfeat).max(), np.abs(o_rec - np.concatenate(recon)).max(), abs(o_fd - fd), abs(o_fdist - feat_dist)))
+    assert np.abs(o_feat - gfeat).max() < 1e-5 and np.abs(o_rec - np.concatenate(recon)).max() < 1e-5
+    assert abs(o_fd - fd) < 1e-9 * max(1, abs(fd)) and abs(o_fdist - feat_dist) < 1e-9
+    path = os.path.join(OUT, "s2ag_fgd_golden.npz")
+    np.savez_compressed(path, weight_seed=777, pair_seed=4321, n_batches=n_batches, batch=nb, gen_feat=gfeat,
+                        real_feat=rfeat, gen_recon_b0=recon[0][:6], recon_err_diff=np.array(ev.recon_err_diff),
+                        frechet=np.float64(fd), feat_dist=np.float64(feat_dist),
+                        keys=np.array(sorted(net.state_dict().keys())))
+    print("wrote", path, os.path.getsize(path), "bytes; FGD %.6f feat_dist %.6f" % (fd, feat_dist))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["step", "longform", "checkpoints"]
+    what = sys.argv[1:] or ["step", "longform", "checkpoints", "fgd"]
     if "step" in what:
         main()
     if "longform" in what:
         longform()
     if "checkpoints" in what:
         checkpoints()
+    if "fgd" in what:
+        fgd()

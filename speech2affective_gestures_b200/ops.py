@@ -1012,3 +1012,34 @@ def pose_metrics(out, target, mean, n_pre, dst=None):
     ws = torch.empty(3, dtype=torch.float64, device=out.device)
     _C.call("s2ag_pose_metrics", _p(out), _p(target), _p(mean), _p(ws), _p(dst), B, T, int(n_pre), _stream(out))
     return dst
+
+
+# ------------------------------------------------------------------------------------------ Frechet gesture distance
+def fgd_new_accumulator(device, D=32):
+    """zeroed fp64 moment buffer of s2ag_fgd_accumulate (net/embedding_space_evaluator.py:28-40: the four host lists)"""
+    return torch.zeros(int(_C.lib().s2ag_fgd_acc_doubles(int(D))), dtype=torch.float64, device=device)
+
+
+def fgd_accumulate(acc, gen_feat, real_feat):
+    """net/embedding_space_evaluator.py:45-57 without the D2H copies: fold [N, D] feature pairs into `acc`."""
+    _check(gen_feat, real_feat)
+    N, D = gen_feat.shape
+    assert real_feat.shape == gen_feat.shape and gen_feat.stride(1) == 1 and real_feat.stride(1) == 1
+    _C.call("s2ag_fgd_accumulate", _p(gen_feat), gen_feat.stride(0), _p(real_feat), real_feat.stride(0), N, D, _p(acc),
+            _stream(gen_feat))
+
+
+def fgd_scores(acc, D=32):
+    """net/embedding_space_evaluator.py:73-101 -> float64[2] device tensor (frechet_dist, feat_dist)"""
+    out = torch.empty(2, dtype=torch.float64, device=acc.device)
+    _C.call("s2ag_fgd_scores", _p(acc), int(D), _p(out), _stream(acc))
+    return out
+
+
+def frechet_distance(mu1, sigma1, mu2, sigma2):
+    """net/embedding_space_evaluator.py:104-152 for given moments (fp64 device tensors) -> float64[2], [0] = distance"""
+    D = mu1.numel()
+    ts = [t.to(torch.float64).contiguous() for t in (mu1, sigma1, mu2, sigma2)]
+    out = torch.empty(2, dtype=torch.float64, device=ts[0].device)
+    _C.call("s2ag_frechet_distance", _p(ts[0]), _p(ts[1]), _p(ts[2]), _p(ts[3]), int(D), _p(out), _stream(ts[0]))
+    return out

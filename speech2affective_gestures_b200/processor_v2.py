@@ -4,7 +4,10 @@ constructor, `forward_pass_s2ag` (one GAN iteration, :776-957), `per_train_epoch
 `generate_gestures_by_dataset` (:1441-1567); the long-form entry points render clips in lock-step batches on the
 device (longform.py).
 
-Out of scope: LMDB/npz cache writers, video rendering, FGD evaluator, BVH export.
+The FGD evaluators (`EmbeddingSpaceEvaluator`, :162-165) are built when `outputs/embedding_net.pth.tar` exists under
+base_path and accumulate on the device (net/embedding_space_evaluator.py, csrc/fgd.cu).
+
+Out of scope: LMDB/npz cache writers, video rendering, BVH export.
 
 Execution model (B200-first): one process per GPU; every kernel of a step is enqueued on one
 stream with no host synchronisation (the reference's ~9 `.item()` syncs per step, :943-956, become
@@ -23,6 +26,7 @@ import torch.distributed as dist
 
 from . import ops
 from .net import embedding_net as en
+from .net.embedding_space_evaluator import EmbeddingSpaceEvaluator
 from .net.multimodal_context_net_v2 import PoseGeneratorTriModal as PGT, ConvDiscriminatorTriModal as CDT, \
     PoseGenerator, AffDiscriminator
 
@@ -120,6 +124,12 @@ class Processor(object):
         for net in (self.trimodal_generator, self.trimodal_discriminator, self.s2ag_generator,
                     self.s2ag_discriminator):
             net.to(self.device)
+
+        # processor_v2.py:162-165; the reference fails without the checkpoint, here the evaluators are simply absent
+        self.evaluator_trimodal = self.evaluator = None
+        if base_path and os.path.isfile(os.path.join(base_path, 'outputs/embedding_net.pth.tar')):
+            self.evaluator_trimodal = EmbeddingSpaceEvaluator(base_path, cfg, pose_dim, self.lang_model, self.device)
+            self.evaluator = EmbeddingSpaceEvaluator(base_path, cfg, pose_dim, self.lang_model, self.device)
 
         self.train_samples = self.data_loader['train_data_s2ag'].samples
         self.val_samples = self.data_loader['val_data_s2ag'].samples
@@ -681,8 +691,8 @@ class Processor(object):
                           s2ag_epoch='best', make_video=False, calculate_metrics=True):
         """34-frame batched evaluation (processor_v2.py:1071-1142): eval mode, batch 2048, the full step under
         no_grad; L1 / joint MAE / acceleration difference of `push_samples` (:738-774) are reduced on the device
-        (csrc/longform.cu) and read back once at the end.  Returns the reference's loss_dict (plus 'accel*', 'clips').
-        FGD (EmbeddingSpaceEvaluator) needs an external checkpoint and is out of scope."""
+        (csrc/longform.cu) and read back once at the end, and so are the two FGD evaluators when the embedding-net
+        checkpoint exists (:750-751, :1116-1136).  Returns the reference's loss_dict (plus 'accel*', 'clips')."""
         if make_video:
             raise NotImplementedError("video rendering is outside the hot path (SURVEY 8)")
         if load_saved_model:
@@ -711,13 +721,25 @@ class Processor(object):
                 if calculate_metrics:
                     acc[0] += ops.pose_metrics(self.last_out, vec, mean, cfg.n_pre_poses) * len(keys)
                     acc[1] += ops.pose_metrics(self.last_out_trimodal, vec, mean, cfg.n_pre_poses) * len(keys)
+                    if self.evaluator_trimodal:   # push_samples(:750-751): (text, audio, generated, target)
+                        self.evaluator_trimodal.push_samples(text, audio, self.last_out_trimodal, vec)
+                    if self.evaluator:
+                        self.evaluator.push_samples(text, audio, self.last_out, vec)
         (l1, mae, accel), (l1_t, mae_t, accel_t) = (acc / max(n, 1)).tolist()
+        loss_dict = {'loss_trimodal': l1_t, 'joint_mae_trimodal': mae_t, 'loss': l1, 'joint_mae': mae,
+                     'accel_trimodal': accel_t, 'accel': accel, 'clips': n}
         elapsed = time.time() - start_time
-        print('[VAL Trimodal]\tloss: {:.3f}, joint mae: {:.3f} / {:.1f}s'.format(l1_t, mae_t, elapsed))
-        print('[VAL Ours]\t\tloss: {:.3f}, joint mae: {:.3f} / {:.1f}s'.format(l1, mae, elapsed))
+        for tag, ev, sfx, vals in (('[VAL Trimodal]\t', self.evaluator_trimodal, '_trimodal', (l1_t, mae_t, accel_t)),
+                                   ('[VAL Ours]\t\t', self.evaluator, '', (l1, mae, accel))):
+            if ev and ev.get_no_of_samples() > 0:
+                fd, feat_d = ev.get_scores()
+                print(tag + 'loss: {:.3f}, joint mae: {:.5f}, accel diff: {:.5f},FGD: {:.3f}, feat_D: {:.3f} / {:.1f}s'
+                      .format(vals[0], vals[1], vals[2], fd, feat_d, elapsed))
+                loss_dict['frechet' + sfx], loss_dict['feat_dist' + sfx] = fd, feat_d
+            else:
+                print(tag + 'loss: {:.3f}, joint mae: {:.3f} / {:.1f}s'.format(vals[0], vals[1], elapsed))
         print('Total time taken: {:.2f} seconds.'.format(time.time() - start_time))
-        return {'loss_trimodal': l1_t, 'joint_mae_trimodal': mae_t, 'loss': l1, 'joint_mae': mae,
-                'accel_trimodal': accel_t, 'accel': accel, 'clips': n}
+        return loss_dict
 
     def _check_speaker_ids(self, vids):
         """nn.Embedding device-asserts on an out-of-range id (and so does csrc/tcn.cu); fail on the host with a message
