@@ -178,6 +178,15 @@ int s2ag_wavencoder_fwd(const float* audio, int B, int L, const float* const* co
  * x[M, V, K*C] (channel index k*C + c), A[K,V,V], y[M, V, C]:  y[m,w,c] = sum_{k,v} x[m,v,k*C+c] A[k,v,w] */
 int s2ag_graph_fwd(const float* x, const float* A, float* y, int M, int V, int K, int C, void* stream);
 int s2ag_graph_bwd(const float* dy, const float* A, float* dx, int M, int V, int K, int C, void* stream);
+/* ConvTemporalGraphical (tgcn.py:15-71) as one temporal convolution: the (Kt x 1) Conv2d Cin -> K*C (weight W[K*C, Cin, Kt],
+ * bias b) composed with the adjacency contraction is the Conv1d x[n, t, v*Cin + ci] -> y[n, t, w*C + c] with
+ *   Weff[w*C + c][v*Cin + ci][dt] = sum_k A[k,v,w] W[k*C + c][ci][dt],   beff[w*C + c] = sum_k (sum_v A[k,v,w]) b[k*C + c]
+ * (run it through s2ag_conv_fwd / _bwd_data / _bwd_weight).  _bwd folds the gradients of the composed tensors back:
+ * dW += A-contraction of dWeff, db += ... (db / dbeff may be NULL). */
+int s2ag_gcn_compose_fwd(const float* W, const float* b, const float* A, float* Weff, float* beff, int V, int K,
+                         int C, int Cin, int Kt, void* stream);
+int s2ag_gcn_compose_bwd(const float* dWeff, const float* dbeff, const float* A, float* dW, float* db, int V,
+                         int K, int C, int Cin, int Kt, void* stream);
 
 /* ---- weight_norm + causal dilated TemporalBlock (net/tcn.py:16-46) ---------------------------
  * weight_norm (old style, dim=0): w[co] = g[co] * v[co] / ||v[co]||.  v is [Co,Ci,k] (reference

@@ -7,7 +7,11 @@ Sequential(Conv2d 1x1, BN2d).  The nn.* objects are parameter containers only; c
 through ops.* (libs2ag_b200.so)."""
 import torch.nn as nn
 
+import os
+
 from ... import ops
+
+COMPOSED = os.environ.get("S2AG_GCN_COMPOSED", "1") != "0"   # A/B switch: 0 = two-kernel route (conv, then contraction)
 
 
 class ConvTemporalGraphical(nn.Module):
@@ -23,6 +27,10 @@ class ConvTemporalGraphical(nn.Module):
 
     def forward(self, x, A):
         """x [N,T,V,Cin] -> [N,T,V,Cout];  einsum('nkctv,kvw->nctw') of the reference (:66-69)."""
+        if COMPOSED:
+            # conv and adjacency contraction composed into one temporal convolution over [N, T, V*Cin] rows: the
+            # [N, T, V, K*Cout] intermediate (25 MB at 256 clips) is never formed (ops.GcnFn)
+            return ops.gcn_conv(x, self.conv.weight, self.conv.bias, A, self.geom[2]), A
         y = ops.conv_bn_act(x, self.conv.weight, self.conv.bias, self.geom)
         return ops.graph_contract(y, A), A
 

@@ -8,6 +8,7 @@ Layout convention (see include/s2ag.h): activations are channels-last; parameter
 ACCUMULATED by the kernels straight into `param.grad` (which the network modules alias onto one
 flat buffer per network), so the backward functions return None for parameters.
 """
+import contextlib
 import ctypes
 import itertools
 import os
@@ -519,6 +520,74 @@ class GraphFn(torch.autograd.Function):
 
 def graph_contract(x, A):
     return GraphFn.apply(x, A)
+
+
+class GcnFn(torch.autograd.Function):
+    """ConvTemporalGraphical (net/utils/tgcn.py:15-71) as ONE temporal convolution: the (Kt x 1) Conv2d Cin -> K*C and
+    einsum('nkctv,kvw->nctw') are composed into a Conv1d over the channels-last rows [N, T, V*Cin] -> [N, T, V*C]
+    (s2ag_gcn_compose_fwd builds the composed weight every call: the weights change every step), so the [N, T, V, K*C]
+    intermediate is never written.  Backward: data gradient and weight gradient of that Conv1d, then the composed
+    weight gradient is folded back onto the Conv2d's parameters (s2ag_gcn_compose_bwd, += into their .grad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, A, pad):
+        _check(x, w, b, A)
+        N, T, V, Cin = x.shape
+        K = A.shape[0]
+        KC, _, Kt, _ = w.shape
+        C = KC // K
+        x = x.contiguous()
+        st = _stream(x)
+        weff = _empty((V * C, V * Cin, Kt), x)
+        beff = _empty((V * C,), x)
+        _C.call("s2ag_gcn_compose_fwd", _p(w), _p(b), _p(A), _p(weff), _p(beff), V, K, C, Cin, Kt, st)
+        y = _empty((N, T, V, C), x)
+        _C.call("s2ag_conv_fwd", _p(x), V * Cin, N, T, 1, V * Cin, _p(weff), _p(beff), _p(y), V * C, V * C, Kt, 1, 1, 1,
+                int(pad), 0, 1, 1, ACT_NONE, 0.0, st)
+        ctx.t = (x, w, b, A, weff)
+        ctx.dims = (N, T, V, Cin, K, C, Kt, int(pad))
+        ctx.want_w = w.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, A, weff = ctx.t
+        N, T, V, Cin, K, C, Kt, pad = ctx.dims
+        dy = dy.contiguous()
+        st = _stream(dy)
+        if ctx.want_w:
+            side = _side_stream[0]
+            cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
+            wst = st
+            if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:
+                ev = torch.cuda.Event()   # weight gradient beside the data-gradient chain (see ConvBnActFn.backward)
+                ev.record(cur)
+                side.wait_event(ev)
+                wst = _handle(side, dy.device)
+                for t_ in (dy, x):
+                    t_.record_stream(side)
+                ctxm = torch.cuda.stream(side)
+            else:
+                ctxm = contextlib.nullcontext()
+            with ctxm:
+                dweff = torch.zeros_like(weff)
+                dbeff = torch.zeros(V * C, dtype=torch.float32, device=dy.device)
+            has_b = b is not None and b.requires_grad
+            _C.call("s2ag_conv_bwd_weight", _p(dy), V * C, _p(x), V * Cin, N, T, 1, V * Cin, _p(dweff), _p(dbeff), V * C,
+                    Kt, 1, 1, 1, pad, 0, 1, 1, wst)
+            _C.call("s2ag_gcn_compose_bwd", _p(dweff), _p(dbeff), _p(A), _p(_grad_of(w)),
+                    _p(_grad_of(b)) if has_b else None, V, K, C, Cin, Kt, wst)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty(x.shape, dy)
+            _C.call("s2ag_conv_bwd_data", _p(dy), V * C, N, T, 1, V * Cin, _p(weff), _p(dx), V * Cin, V * C, Kt, 1, pad, 0,
+                    1, 1, 0, st)
+        return dx, None, None, None, None
+
+
+def gcn_conv(x, w, b, A, pad):
+    """x [N, T, V, Cin] -> [N, T, V, C]; w / b: the reference's gcn.conv parameters, A [K, V, V]"""
+    return GcnFn.apply(x, w, b, A, pad)
 
 
 # ------------------------------------------------------------------------------------------ Embedding

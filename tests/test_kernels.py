@@ -212,6 +212,33 @@ def test_graph_contract(dev):
     close(y, ref); close(xd.grad, xr.grad, what="dx")
 
 
+@pytest.mark.parametrize("V,Cin,B", [(9, 3, 2), (3, 48, 2), (9, 3, 33)])
+def test_gcn_composed_conv(dev, V, Cin, B):
+    """ConvTemporalGraphical as one composed temporal convolution (ops.GcnFn) vs Conv2d((9,1)) + einsum of the reference
+    (net/utils/tgcn.py:52-69): output, input gradient, gradients of the ORIGINAL conv parameters (accumulated: a second
+    backward doubles them)"""
+    torch.manual_seed(60 + V)
+    T, K, C = 34, 5, 16
+    conv = nn.Conv2d(Cin, K * C, (9, 1), padding=(4, 0))
+    A = torch.rand(K, V, V)
+    A[-1] = 0   # the body-part graph's last partition is all-zero (SURVEY 8 a6)
+    x = torch.randn(B, T, V, Cin)
+    xr = P(x, "cpu")
+    yr = conv(xr.permute(0, 3, 1, 2))                     # n (k c) t v
+    n, kc, t, v = yr.shape
+    ref = torch.einsum("nkctv,kvw->nctw", yr.view(n, K, C, t, v), A).permute(0, 2, 3, 1)   # n t w c
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    w, b = P(conv.weight.detach(), dev), P(conv.bias.detach(), dev)
+    xd = P(x, dev)
+    for rep in (1, 2):
+        xd.grad = None
+        y = ops.gcn_conv(xd, w, b, A.to(dev), 4)
+        y.backward(g.to(dev))
+        close(y, ref); close(xd.grad, xr.grad, what="dx")
+        close(w.grad, rep * conv.weight.grad, what="dW"); close(b.grad, rep * conv.bias.grad, what="db")
+
+
 @pytest.mark.parametrize("d", [1, 2, 4, 8])
 def test_tcn_block(dev, d):
     from torch.nn.utils import weight_norm
