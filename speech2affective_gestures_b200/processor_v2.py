@@ -37,6 +37,17 @@ ops.manual_seed(1234)
 M_DIS, M_HUBER, M_GEN, M_KLD, M_DIV, M_TOTAL, M_L1, M_L1_TRI = range(8)
 
 
+def _prio(role):
+    """Stream priorities of the captured step (CUDA: lower number = scheduled first when SMs free up).  The main stream
+    carries the serial D step / D(out) / loss chain of short kernels; the side streams carry wide, latency-tolerant
+    work (weight-gradient GEMMs, the other generator passes) that must not starve it.  S2AG_STREAM_PRIO="m,a,b"
+    overrides (A/B measurements)."""
+    env = os.environ.get("S2AG_STREAM_PRIO")
+    table = dict(zip(("main", "side", "sideb"), (int(v) for v in env.split(",")))) if env else \
+        dict(main=-1, side=0, sideb=0)   # measured: 12.94 -> 12.50 ms/step (tools/ab_schedule.sh)
+    return table[role]
+
+
 def get_epoch_and_loss(path_to_model_files, epoch='best'):
     """Checkpoint discovery by filename, same scheme as processor_v2.py:53-83:
     epoch_{:06d}_loss_{:.4f}_model.pth.tar; 'best' = lowest loss."""
@@ -205,11 +216,11 @@ class Processor(object):
         use_side = self.device.type == "cuda" and self.use_side_stream
         main_s = torch.cuda.current_stream() if use_side else None
         txt1 = txt2 = txt3 = tri_pre = None
-        eps2 = eps3 = early3 = early2 = None
+        eps2 = eps3 = early3 = early2 = run_tri_late = out_tri = None
         ev = {}
         if use_side:
             if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream()
+                self._side_stream = torch.cuda.Stream(priority=_prio("side"))
             side = self._side_stream
             ops.set_side_stream(side)  # GRU weight-gradient GEMMs run there, beside the next layer's BPTT kernel
             side.wait_stream(main_s)
@@ -247,7 +258,7 @@ class Processor(object):
                 # for it before generator pass #2, so two generator-sized persistent kernels (76 + 76 > 148 SMs) can
                 # never be in flight together.
                 if self._side_stream_b is None:
-                    self._side_stream_b = torch.cuda.Stream()
+                    self._side_stream_b = torch.cuda.Stream(priority=_prio("sideb"))
                 sb = self._side_stream_b
                 ev_p1 = torch.cuda.Event(); ev_p1.record(main_s)
                 sb.wait_event(ev_p1)
@@ -269,58 +280,70 @@ class Processor(object):
                             t_.record_stream(sb)
                     return o
 
-                tri_late = train  # training: generator passes #3 / #2 first, the baseline beside D(out) (below)
+                # training: generator pass #2, then #3 on this stream beside the D step; the frozen baseline is queued
+                # behind the generator's BPTT (after autograd.backward below), beside the encoders' backward
+                tri_mode = os.environ.get("S2AG_TRI_LATE", "mid") if train else "0"   # A/B: "0" first, "1" after the BPTT
+                tri_late = tri_mode != "0"
                 if not tri_late:
                     out_tri = run_tri()
                     ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
                 pre_seq.record_stream(sb)
-                if use_div and train:
-                    # Generator pass #3 (the no-grad style-diversity pass, :903-910) depends on nothing the D step or
-                    # pass #2 produce: it follows the baseline on the same side stream, still beside the D step.  The
-                    # re-parametrisation noise of passes #2 and #3 is drawn here, in the reference's order.
-                    if cfg.z_type == 'speaker':
-                        like = torch.empty(vid_indices.shape[0], G.z_size, device=self.device)
-                        eps2, eps3 = en.draw_eps(like), en.draw_eps(like)
-                        rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
-                            torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
-                        rand_vids = vid_indices[rand_idx]
-                    else:
-                        rand_vids = None
-                    ev_r = torch.cuda.Event(); ev_r.record(main_s)
-                    sb.wait_event(ev_r)
-                    sb.wait_event(ev[3])
-                    with torch.cuda.stream(sb):
-                        with torch.no_grad():
-                            early3 = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng, text_feat=txt3, eps=eps3)
-                    ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
-                    for t_ in shared_ng + (txt3, rand_vids, eps3, in_text, in_mfcc):
-                        if t_ is not None:
-                            t_.record_stream(sb)
-                    for t_ in early3:
-                        if t_ is not None:
-                            t_.record_stream(main_s)
-                if train:
-                    # Generator pass #2 (the forward of the G step, :823) does not depend on the D update either (only
-                    # D(out) after it does): it follows on the same side stream, so the G step on the main stream starts
-                    # at D(out).  autograd runs its backward (BPTT) on this stream and orders it against the rest.
+                if use_div and train and cfg.z_type == 'speaker':
+                    # the re-parametrisation noise of passes #2 and #3 and the speaker permutation are drawn here, in
+                    # the reference's order (:823, :903-909), whatever order the passes are launched in
+                    like = torch.empty(vid_indices.shape[0], G.z_size, device=self.device)
+                    eps2, eps3 = en.draw_eps(like), en.draw_eps(like)
+                    rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
+                        torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
+                    rand_vids = vid_indices[rand_idx]
+                else:
+                    rand_vids = None
+                def launch_pass2():
+                    # Generator pass #2 (the forward of the G step, :823) does not depend on the D update (only D(out)
+                    # after it does).  autograd runs its backward (BPTT) on this stream and orders it against the rest.
+                    nonlocal early2
                     sb.wait_event(ev[2])
                     ev_m = torch.cuda.Event(); ev_m.record(main_s)
                     sb.wait_event(ev_m)
                     with torch.cuda.stream(sb):
                         early2 = G(pre_seq, in_text, in_mfcc, vid_indices, shared=shared, text_feat=txt2, eps=eps2)
-                    ev['tdone'] = torch.cuda.Event(); ev['tdone'].record(sb)
+                    ev['p2done'] = torch.cuda.Event(); ev['p2done'].record(sb)
                     for t_ in tuple(shared) + (txt2, vid_indices, eps2, in_text, in_mfcc):
                         if t_ is not None:
                             t_.record_stream(sb)
                     for t_ in early2:
                         if t_ is not None:
                             t_.record_stream(main_s)
-                if tri_late:
-                    # The frozen baseline last: its generator-sized recurrent kernels then run beside the D(out) chain
-                    # of the G step (discriminator-sized kernels); its output is only needed by the final metric.  The
-                    # main stream joins this stream before the end of the step, and the generator's BPTT kernels are
-                    # queued behind it on this same stream.
+
+                def launch_pass3():
+                    # Generator pass #3 (the no-grad style-diversity pass, :903-910) depends on nothing the D step or
+                    # pass #2 produce and is only needed by the loss.
+                    nonlocal early3
+                    ev_r = torch.cuda.Event(); ev_r.record(main_s)
+                    sb.wait_event(ev_r)
+                    sb.wait_event(ev[3])
+                    with torch.cuda.stream(sb):
+                        with torch.no_grad():
+                            early3 = G(pre_seq, in_text, in_mfcc, rand_vids, shared=shared_ng, text_feat=txt3, eps=eps3)
+                    ev['p3done'] = torch.cuda.Event(); ev['p3done'].record(sb)
+                    for t_ in shared_ng + (txt3, rand_vids, eps3, in_text, in_mfcc):
+                        if t_ is not None:
+                            t_.record_stream(sb)
+                    for t_ in early3:
+                        if t_ is not None:
+                            t_.record_stream(main_s)
+
+                # order on the side stream (measured, tools/step_timeline.py): pass #3, pass #2, then the baseline
+                order = os.environ.get("S2AG_PASS_ORDER", "32")
+                for which in order:
+                    if which == "2" and train:
+                        launch_pass2()
+                    elif which == "3" and use_div and train:
+                        launch_pass3()
+                if tri_mode == "mid":
                     out_tri = run_tri()
+                elif tri_late:
+                    run_tri_late = run_tri
             with torch.set_grad_enabled(train):
                 dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
@@ -337,13 +360,15 @@ class Processor(object):
             G.zero_grad()
         if use_side and 'tdone' in ev:
             main_s.wait_event(ev['tdone'])
-        else:
+        elif run_tri_late is None and out_tri is None:
             if use_side:
                 main_s.wait_event(ev['t'])
             with torch.no_grad():
                 out_tri, *_ = Tri(pre_seq, in_text, in_audio, vid_indices, pre=tri_pre)
         if use_side:
             main_s.wait_event(ev[2])
+            if 'p2done' in ev:
+                main_s.wait_event(ev['p2done'])
         with torch.set_grad_enabled(train):
             if early2 is not None:
                 out, z, z_mu, z_log_var = early2
@@ -362,6 +387,7 @@ class Processor(object):
                     p.requires_grad_(True)
         out_rand = z_rand = None
         if early3 is not None:
+            main_s.wait_event(ev['p3done'])
             out_rand, z_rand = early3[0], early3[1]
         elif use_div:
             if cfg.z_type == 'speaker':
@@ -396,9 +422,17 @@ class Processor(object):
                 main_s.wait_stream(self._side_stream)
                 if self._side_stream_b is not None:
                     main_s.wait_stream(self._side_stream_b)
+                if run_tri_late is not None:
+                    # the frozen baseline, queued behind the generator's BPTT kernels on the second side stream (two
+                    # generator-sized persistent kernels never share the SMs): it runs beside the all-reduce / Adam
+                    # tail and is joined below; only the final metric reads its output
+                    out_tri = run_tri_late()
+                    run_tri_late = None
             self._allreduce_grads(G)
             ops.adam_step(G.flat_params, G.flat_grads, self.gen_m, self.gen_v, self.lr_s2ag_gen, 0.5, 0.999, 1e-8,
                           self.gen_step, 1.0 / self.world)
+        if run_tri_late is not None:   # (no backward pass ran: not reachable in training, kept for safety)
+            out_tri = run_tri_late()
         if use_side:
             main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
             if self._side_stream_b is not None:
@@ -442,7 +476,7 @@ class Processor(object):
         # the packed-operand contractions is registered for it before the capture starts (ops._handle never allocates
         # during a capture; a stream first seen while capturing would fall back to the unpacked contraction).
         if getattr(self, "_capture_stream", None) is None:
-            self._capture_stream = torch.cuda.Stream()
+            self._capture_stream = torch.cuda.Stream(priority=_prio("main"))
         cs = self._capture_stream
         snap = self._snapshot_state() if train else None   # warm-up iterations must not train the live model
         cs.wait_stream(torch.cuda.current_stream())
