@@ -243,12 +243,16 @@ class _BnState:
 
 _bn_repeat = [1]
 _side_stream = [None]
+_side_stream_conv = [None]
 
 
-def set_side_stream(stream):
+def set_side_stream(stream, conv_stream=None):
     """Second CUDA stream for work that is off the critical path of the recurrent kernels (weight-gradient GEMMs of a
-    GRU layer).  The caller must make its main stream wait for it before consuming parameter gradients."""
+    GRU layer).  `conv_stream` (default: the same stream): where the weight gradients of the convolutions go -- a stream
+    of their own keeps them from queueing behind the text encoder's backward and the GRU weight gradients.  The caller
+    must make its main stream wait for both before consuming parameter gradients."""
     _side_stream[0] = stream
+    _side_stream_conv[0] = conv_stream if conv_stream is not None else stream
 
 
 
@@ -422,7 +426,7 @@ class ConvBnActFn(torch.autograd.Function):
         w, b = ctx.w, ctx.b
         if ctx.want_w:
             db = _grad_of(b) if (b is not None and b.requires_grad) else None
-            side = _side_stream[0]
+            side = _side_stream_conv[0]
             cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
             wst = st
             if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:
@@ -556,7 +560,7 @@ class GcnFn(torch.autograd.Function):
         dy = dy.contiguous()
         st = _stream(dy)
         if ctx.want_w:
-            side = _side_stream[0]
+            side = _side_stream_conv[0]
             cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
             wst = st
             if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:

@@ -155,6 +155,7 @@ class Processor(object):
         self.metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
         self._side_stream = None
+        self._side_stream_c = None
         self._side_stream_b = None
         self._copy_stream = None
         self.use_side_stream = True
@@ -222,8 +223,14 @@ class Processor(object):
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(priority=_prio("side"))
             side = self._side_stream
-            ops.set_side_stream(side)  # GRU weight-gradient GEMMs run there, beside the next layer's BPTT kernel
+            if self._side_stream_c is None and os.environ.get("S2AG_CONV_WGRAD_STREAM", "1") != "0":
+                self._side_stream_c = torch.cuda.Stream(priority=_prio("side"))
+            # GRU weight-gradient GEMMs run on `side`, beside the next layer's BPTT kernel; the convolutions' weight
+            # gradients on a stream of their own (they would otherwise queue behind the text encoder's backward)
+            ops.set_side_stream(side, self._side_stream_c)
             side.wait_stream(main_s)
+            if self._side_stream_c is not None:
+                self._side_stream_c.wait_stream(main_s)
             with torch.cuda.stream(side):
                 if gan_on:
                     with torch.no_grad():
@@ -350,7 +357,9 @@ class Processor(object):
             if train:
                 torch.autograd.backward([dis_real, dis_fake], [g_real, g_fake])
                 if use_side:
-                    main_s.wait_stream(self._side_stream)  # weight-gradient GEMMs issued on the side stream
+                    main_s.wait_stream(self._side_stream)  # weight-gradient GEMMs issued on the side streams
+                    if self._side_stream_c is not None:
+                        main_s.wait_stream(self._side_stream_c)
                 self._allreduce_grads(D)
                 ops.adam_step(D.flat_params, D.flat_grads, self.dis_m, self.dis_v, self.lr_s2ag_dis, 0.5, 0.999,
                               1e-8, self.dis_step, 1.0 / self.world)
@@ -420,6 +429,8 @@ class Processor(object):
                 # the text-encoder backward (and its in-kernel parameter-gradient accumulation) ran on the side stream,
                 # the generator's own backward on the second one
                 main_s.wait_stream(self._side_stream)
+                if self._side_stream_c is not None:
+                    main_s.wait_stream(self._side_stream_c)
                 if self._side_stream_b is not None:
                     main_s.wait_stream(self._side_stream_b)
                 if run_tri_late is not None:
@@ -435,6 +446,8 @@ class Processor(object):
             out_tri = run_tri_late()
         if use_side:
             main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
+            if self._side_stream_c is not None:
+                main_s.wait_stream(self._side_stream_c)
             if self._side_stream_b is not None:
                 main_s.wait_stream(self._side_stream_b)
             ops.set_side_stream(None)
@@ -487,7 +500,9 @@ class Processor(object):
         torch.cuda.synchronize()
         if snap is not None:
             self._restore_state(snap)
-        for st in (cs, self._side_stream, self._side_stream_b):
+        for st in (cs, self._side_stream, self._side_stream_b, self._side_stream_c):
+            if st is not None:
+                ops._handle(st, dev)   # registers the packed-operand scratch of a stream the warm-up did not launch on
             assert st is None or ops.has_scratch(st, dev), "a stream of the captured step has no registered scratch"
         import gc
         gc.collect()  # no autograd graph of the warm-up passes may survive into the capture
