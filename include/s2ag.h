@@ -207,6 +207,13 @@ int s2ag_tcn_block_fwd(const float* x, const float* w1, const float* b1, const f
 int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const float* y2, const float* out,
                        const float* w1, const float* w2, float* dx, float* dw1, float* db1, float* dw2,
                        float* db2, float* ws, int B, int T, int C, int dilation, float p_drop, void* stream);
+/* the same in phases: 1 = data path (dx; leaves the g2 / g1 planes in ws), 2 = parameter path (dw1, db1, dw2, db2 from
+ * ws), 3 = both.  Phase 2 may run on another stream, ordered after phase 1 by an event (pointers a phase does not use
+ * may be NULL). */
+int s2ag_tcn_block_bwd_phased(const float* dout, const float* x, const float* y1, const float* y2, const float* out,
+                              const float* w1, const float* w2, float* dx, float* dw1, float* db1, float* dw2,
+                              float* db2, float* ws, int B, int T, int C, int dilation, float p_drop, int phases,
+                              void* stream);
 
 /* ---- nn.Embedding (+ nn.Dropout) (:70-73,:88; :470-472) ------------------------------------- */
 int s2ag_embedding_fwd(const int64_t* idx, const float* table, float* out, long ldo, long n, int D, long V,

@@ -162,52 +162,70 @@ extern "C" int s2ag_tcn_block_fwd(const float* x, const float* w1, const float* 
   return S2AG_OK;
 }
 
-extern "C" int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const float* y2,
-                                  const float* out, const float* w1, const float* w2, float* dx, float* dw1,
-                                  float* db1, float* dw2, float* db2, float* ws, int B, int T, int C, int dilation,
-                                  float p_drop, void* stream) {
-  S2AG_CHECK_ARG(dout && x && y1 && y2 && out && w1 && w2 && dx && dw1 && db1 && dw2 && db2 && ws);
+// phases: 1 = data path (head kernel, g1 = dgrad(g2; W2), dx += dgrad(g1; W1)), 2 = parameter path (dw2, db2, dw1, db1;
+// reads the g2 / g1 planes phase 1 left in ws), 3 = both.  A caller may run phase 2 on another stream, ordered after
+// phase 1 by an event, so that the weight gradients leave the data-gradient chain of the text encoder.
+extern "C" int s2ag_tcn_block_bwd_phased(const float* dout, const float* x, const float* y1, const float* y2,
+                                         const float* out, const float* w1, const float* w2, float* dx, float* dw1,
+                                         float* db1, float* dw2, float* db2, float* ws, int B, int T, int C,
+                                         int dilation, float p_drop, int phases, void* stream) {
+  S2AG_CHECK_ARG(x && y1 && w1 && w2 && ws && (phases & 3) && !(phases & ~3));
+  S2AG_CHECK_ARG(!(phases & 1) || (dout && y2 && out && dx));
+  S2AG_CHECK_ARG(!(phases & 2) || (dw1 && db1 && dw2 && db2));
   S2AG_CHECK_ARG(B >= 0 && T > 0 && C > 0 && dilation > 0 && p_drop >= 0.f && p_drop < 1.f);
   const int M = B * T, K = 2 * C;
   if (M == 0) return S2AG_OK;
   const long n = (long)M * C;
   const float scale = 1.f / (1.f - p_drop);
   float* g2 = ws; float* g1 = ws + n;
-  {
-    int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    auto kfn = &tcn_bwd_head_kernel;
-    S2AG_LAUNCH(kfn, blocks, 256, 0, stream, dout, out, y2, dx, g2, n, scale);
+  if (phases & 1) {
+    {
+      int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+      auto kfn = &tcn_bwd_head_kernel;
+      S2AG_LAUNCH(kfn, blocks, 256, 0, stream, dout, out, y2, dx, g2, n, scale);
+    }
+    // g1 = dgrad(g2; W2) * relu'(y1) * scale
+    {
+      LdWdgrad<ORDER_KKC> b{w2, C, 2, (long)K, 1, (long)C};
+      EpiGeneric e = make_epi(g1, (long)C);
+      e.alpha = scale; e.mul_src = y1; e.ld_mul = C; e.mul_act = S2AG_ACT_RELU;
+      launch_gemm(tcn_loader(g2, T, C, dilation, -1), b, e, M, C, K, 1, 1, stream);
+    }
+    // dx += dgrad(g1; W1)
+    {
+      LdWdgrad<ORDER_KKC> b{w1, C, 2, (long)K, 1, (long)C};
+      launch_gemm(tcn_loader(g1, T, C, dilation, -1), b, make_epi(dx, (long)C, nullptr, 0, 0.f, 1), M, C, K, 1, 1,
+                  stream);
+    }
   }
-  const int sk = pick_splitk(C, K, M, 1);
-  // conv2 weight / bias gradients
-  {
-    LdPlain<false> a{g2, 1, (long)C, 0};
-    LdT<LdConv<ORDER_KKC>> b{tcn_loader(y1, T, C, dilation, +1)};
-    launch_gemm(a, b, make_epi(dw2, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), C, K, M, 1, sk, stream);
-    launch_colsum(g2, C, db2, M, C, stream);
-  }
-  // g1 = dgrad(g2; W2) * relu'(y1) * scale
-  {
-    LdWdgrad<ORDER_KKC> b{w2, C, 2, (long)K, 1, (long)C};
-    EpiGeneric e = make_epi(g1, (long)C);
-    e.alpha = scale; e.mul_src = y1; e.ld_mul = C; e.mul_act = S2AG_ACT_RELU;
-    launch_gemm(tcn_loader(g2, T, C, dilation, -1), b, e, M, C, K, 1, 1, stream);
-  }
-  // conv1 weight / bias gradients
-  {
-    LdPlain<false> a{g1, 1, (long)C, 0};
-    LdT<LdConv<ORDER_KKC>> b{tcn_loader(x, T, C, dilation, +1)};
-    launch_gemm(a, b, make_epi(dw1, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), C, K, M, 1, sk, stream);
-    launch_colsum(g1, C, db1, M, C, stream);
-  }
-  // dx += dgrad(g1; W1)
-  {
-    LdWdgrad<ORDER_KKC> b{w1, C, 2, (long)K, 1, (long)C};
-    launch_gemm(tcn_loader(g1, T, C, dilation, -1), b, make_epi(dx, (long)C, nullptr, 0, 0.f, 1), M, C, K, 1, 1,
-                stream);
+  if (phases & 2) {
+    const int sk = pick_splitk(C, K, M, 1);
+    // conv2 weight / bias gradients
+    {
+      LdPlain<false> a{g2, 1, (long)C, 0};
+      LdT<LdConv<ORDER_KKC>> b{tcn_loader(y1, T, C, dilation, +1)};
+      launch_gemm(a, b, make_epi(dw2, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), C, K, M, 1, sk, stream);
+      launch_colsum(g2, C, db2, M, C, stream);
+    }
+    // conv1 weight / bias gradients
+    {
+      LdPlain<false> a{g1, 1, (long)C, 0};
+      LdT<LdConv<ORDER_KKC>> b{tcn_loader(x, T, C, dilation, +1)};
+      launch_gemm(a, b, make_epi(dw1, (long)K, nullptr, 0, 0.f, sk > 1 ? 2 : 1), C, K, M, 1, sk, stream);
+      launch_colsum(g1, C, db1, M, C, stream);
+    }
   }
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
+}
+
+extern "C" int s2ag_tcn_block_bwd(const float* dout, const float* x, const float* y1, const float* y2,
+                                  const float* out, const float* w1, const float* w2, float* dx, float* dw1,
+                                  float* db1, float* dw2, float* db2, float* ws, int B, int T, int C, int dilation,
+                                  float p_drop, void* stream) {
+  S2AG_CHECK_ARG(dout && x && y1 && y2 && out && w1 && w2 && dx && dw1 && db1 && dw2 && db2 && ws);
+  return s2ag_tcn_block_bwd_phased(dout, x, y1, y2, out, w1, w2, dx, dw1, db1, dw2, db2, ws, B, T, C, dilation, p_drop,
+                                   3, stream);
 }
 
 extern "C" int s2ag_embedding_fwd(const int64_t* idx, const float* table, float* out, long ldo, long n, int D, long V,

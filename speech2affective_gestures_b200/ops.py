@@ -244,15 +244,17 @@ class _BnState:
 _bn_repeat = [1]
 _side_stream = [None]
 _side_stream_conv = [None]
+_side_stream_tcn = [None]
 
 
-def set_side_stream(stream, conv_stream=None):
+def set_side_stream(stream, conv_stream=None, tcn_stream=None):
     """Second CUDA stream for work that is off the critical path of the recurrent kernels (weight-gradient GEMMs of a
     GRU layer).  `conv_stream` (default: the same stream): where the weight gradients of the convolutions go -- a stream
     of their own keeps them from queueing behind the text encoder's backward and the GRU weight gradients.  The caller
     must make its main stream wait for both before consuming parameter gradients."""
     _side_stream[0] = stream
     _side_stream_conv[0] = conv_stream if conv_stream is not None else stream
+    _side_stream_tcn[0] = tcn_stream if tcn_stream is not None else _side_stream_conv[0]   # TCN-block weight gradients
 
 
 
@@ -707,18 +709,37 @@ class TcnBlockFn(torch.autograd.Function):
         st = _stream(dout)
         dout = dout.contiguous()
         dx = _empty(x.shape, x)
-        dw = torch.zeros((2, C, k, C), dtype=torch.float32, device=x.device)
         ws = _empty((2, B * T * C), x)
         train_w = ctx.want_w
-        db1 = _grad_of(b1) if train_w else torch.zeros_like(b1)
-        db2 = _grad_of(b2) if train_w else torch.zeros_like(b2)
-        _C.call("s2ag_tcn_block_bwd", _p(dout), _p(x), _p(y1), _p(y2), _p(out), _p(w1), _p(w2), _p(dx), _p(dw[0]),
-                _p(db1), _p(dw[1]), _p(db2), _p(ws), B, T, C, dilation, p, st)
+        side = _side_stream_tcn[0] if (dout.is_cuda and train_w) else None
+        cur = torch.cuda.current_stream(dout.device) if side is not None else None
+        if side is not None and cur != side:
+            # data path here; the weight gradients (split-K GEMMs, bias sums, weight_norm backward) on the conv
+            # weight-gradient stream, out of the text encoder's data-gradient chain
+            _C.call("s2ag_tcn_block_bwd_phased", _p(dout), _p(x), _p(y1), _p(y2), _p(out), _p(w1), _p(w2), _p(dx), None,
+                    None, None, None, _p(ws), B, T, C, dilation, p, 1, st)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            wst = _handle(side, dout.device)
+            with torch.cuda.stream(side):
+                dw = torch.zeros((2, C, k, C), dtype=torch.float32, device=x.device)
+            for t_ in (ws, x, y1, w1, w2):
+                t_.record_stream(side)
+            _C.call("s2ag_tcn_block_bwd_phased", None, _p(x), _p(y1), None, None, _p(w1), _p(w2), None, _p(dw[0]),
+                    _p(_grad_of(b1)), _p(dw[1]), _p(_grad_of(b2)), _p(ws), B, T, C, dilation, p, 2, wst)
+        else:
+            wst = st
+            dw = torch.zeros((2, C, k, C), dtype=torch.float32, device=x.device)
+            db1 = _grad_of(b1) if train_w else torch.zeros_like(b1)
+            db2 = _grad_of(b2) if train_w else torch.zeros_like(b2)
+            _C.call("s2ag_tcn_block_bwd", _p(dout), _p(x), _p(y1), _p(y2), _p(out), _p(w1), _p(w2), _p(dx), _p(dw[0]),
+                    _p(db1), _p(dw[1]), _p(db2), _p(ws), B, T, C, dilation, p, st)
         if train_w:
             _C.call("s2ag_weight_norm_bwd", _p(dw[0]), _p(v1), _p(g1), _p(n1), _p(_grad_of(v1)), _p(_grad_of(g1)), C, C,
-                    k, st)
+                    k, wst)
             _C.call("s2ag_weight_norm_bwd", _p(dw[1]), _p(v2), _p(g2), _p(n2), _p(_grad_of(v2)), _p(_grad_of(g2)), C, C,
-                    k, st)
+                    k, wst)
         return (dx,) + (None,) * 9
 
 

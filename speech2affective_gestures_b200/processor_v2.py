@@ -227,7 +227,11 @@ class Processor(object):
                 self._side_stream_c = torch.cuda.Stream(priority=_prio("side"))
             # GRU weight-gradient GEMMs run on `side`, beside the next layer's BPTT kernel; the convolutions' weight
             # gradients on a stream of their own (they would otherwise queue behind the text encoder's backward)
-            ops.set_side_stream(side, self._side_stream_c)
+            if self._side_stream_b is None:
+                self._side_stream_b = torch.cuda.Stream(priority=_prio("sideb"))
+            # (the TCN blocks' weight gradients go to the second side stream: it is idle once the generator's BPTT is done)
+            ops.set_side_stream(side, self._side_stream_c,
+                                self._side_stream_b if os.environ.get("S2AG_TCN_WGRAD_STREAM", "b") == "b" else None)
             side.wait_stream(main_s)
             if self._side_stream_c is not None:
                 self._side_stream_c.wait_stream(main_s)
