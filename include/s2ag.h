@@ -140,6 +140,10 @@ int s2ag_bn_fwd(const float* x, long ldx, int M, int C, const float* gamma, cons
                 int training, float momentum, float eps,
                 const float* add, long ldadd, float* y, long ldy, const int32_t* col_map,
                 int act, float slope, float* save_mean, float* save_invstd, double* ws, int groups, void* stream);
+/* A/B switch of the BatchNorm kernels: bit 0 = scalar kernels everywhere (default 0: float4 variants -- 4 channels per
+ * thread, 16-byte loads -- whenever there is no column map, C % 4 == 0 and pitches / pointers are 16-byte aligned).
+ * Returns the previous flags. */
+int s2ag_debug_bn_flags(int flags);
 /* dx = BN'(dy * act'(y)); dgamma += ; dbeta += ; dadd (may be NULL) = dy * act'(y).
  * ws: double[2*C*groups] scratch; groups as in s2ag_bn_fwd. */
 int s2ag_bn_bwd(const float* dy, long lddy, const float* y, long ldy, const int32_t* col_map,

@@ -197,6 +197,66 @@ def test_bn_large_mean(dev):
     close(y, ref, tol=5e-3)
 
 
+@pytest.mark.parametrize("M,C,groups,act,with_add,train", [(1000, 16, 1, 2, True, True), (777, 48, 1, 1, False, True),
+                                                            (1024, 144, 2, 0, False, True), (513, 4, 1, 2, True, True),
+                                                            (300, 64, 1, 2, False, False), (4001, 8, 1, 0, False, True)])
+def test_bn_float4_vs_scalar_and_torch(dev, M, C, groups, act, with_add, train):
+    """the float4 BatchNorm kernels (4 channels per thread) against the scalar kernels (s2ag_debug_bn_flags bit 0) and
+    against F.batch_norm in fp64: output, dx, d(add), dgamma, dbeta, running statistics; ragged row counts, statistics
+    groups (D(real) / D(fake) in one pass), eval mode"""
+    from speech2affective_gestures_b200 import _C
+    torch.manual_seed(90 + C)
+    x = torch.randn(M, C) * 1.5 + 0.7
+    add = torch.randn(M, C) if with_add else None
+    g = torch.randn(M, C)
+    slope = 0.2
+    res = {}
+    for flags in (0, 1):
+        _C.lib().s2ag_debug_bn_flags(flags)
+        try:
+            bn = nn.BatchNorm1d(C)
+            torch.manual_seed(7)
+            with torch.no_grad():
+                bn.weight.copy_(torch.rand(C) + 0.5); bn.bias.copy_(torch.rand(C) - 0.5)
+                bn.running_mean.copy_(torch.rand(C) * 0.4 - 0.2); bn.running_var.copy_(torch.rand(C) + 0.5)
+            bn = bn.to(dev).train(train)
+            xd = P(x, dev)
+            ad = P(add, dev) if with_add else None
+            ctxm = ops.bn_groups(groups) if groups > 1 else __import__("contextlib").nullcontext()
+            with ctxm:
+                y = ops.bn_act(xd, bn, act, slope, add=ad)
+                y.backward(g.to(dev))
+            res[flags] = [t.detach().cpu().clone() for t in (y, xd.grad, bn.weight.grad, bn.bias.grad, bn.running_mean,
+                                                              bn.running_var)] + ([ad.grad.cpu().clone()] if with_add else [])
+        finally:
+            _C.lib().s2ag_debug_bn_flags(0)
+    for a, b, what in zip(res[0], res[1], ("y", "dx", "dgamma", "dbeta", "rmean", "rvar", "dadd")):
+        close(a, b, tol=2e-5, what="float4 vs scalar " + what)
+    # torch reference (fp64), one statistics group at a time
+    xr = x.double().requires_grad_(True)
+    outs = []
+    w64, b64 = res[0][2] * 0, None
+    bnr = nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        torch.manual_seed(7)
+        bnr.weight.copy_(torch.rand(C) + 0.5); bnr.bias.copy_(torch.rand(C) - 0.5)
+    bnr.train(train)
+    if not train:
+        with torch.no_grad():
+            bnr.running_mean.copy_(res[0][4].double()); bnr.running_var.copy_(res[0][5].double())
+    Mg = M // groups
+    for q in range(groups):
+        v = bnr(xr[q * Mg:(q + 1) * Mg])
+        if with_add:
+            v = v + add[q * Mg:(q + 1) * Mg].double()
+        outs.append(v if act == 0 else (F.relu(v) if act == 1 else F.leaky_relu(v, slope)))
+    ref = torch.cat(outs)
+    ref.backward(g.double())
+    close(res[0][0], ref, tol=1e-4, what="y vs torch")
+    close(res[0][1], xr.grad, tol=1e-3, what="dx vs torch")
+    close(res[0][2], bnr.weight.grad, tol=1e-3, what="dgamma vs torch")
+
+
 def test_graph_contract(dev):
     torch.manual_seed(6)
     N, T, V, K, C = 2, 34, 9, 5, 16
