@@ -416,15 +416,31 @@ class PoseGenerator(FlatParamNet, _SpeakerMixin):
         self.do_flatten_parameters = False
         self.flatten_parameters_()
 
-    def encode_shared(self, pre_seq, in_mfcc, repeats=1):
+    def encode_shared(self, pre_seq, in_mfcc, repeats=1, mfcc_stream=None):
         """The dropout-free, BatchNorm-only encoders (AffEncoder on the seed poses, MFCCEncoder): within one GAN
         iteration the reference evaluates them on the SAME inputs with the SAME weights in each of its generator
         passes (processor_v2.py:798, 823, 909), so they are computed once and handed to every pass through
         `forward(..., shared=...)`; `repeats` = number of passes they stand for (BatchNorm running statistics are
         advanced as that many identical updates, see ops.bn_repeat)."""
         with ops.bn_repeat(repeats):
+            a = None
+            if self.input_context in ('both', 'audio'):
+                if mfcc_stream is not None and in_mfcc.is_cuda:
+                    # the two encoders are independent: the MFCC encoder runs on `mfcc_stream` beside the AffEncoder
+                    # (autograd runs its backward there as well); the caller's stream joins before returning
+                    cur = torch.cuda.current_stream(in_mfcc.device)
+                    ev = torch.cuda.Event(); ev.record(cur)
+                    mfcc_stream.wait_event(ev)
+                    with torch.cuda.stream(mfcc_stream):
+                        a = self.audio_encoder(in_mfcc)
+                    done = torch.cuda.Event(); done.record(mfcc_stream)
+                    in_mfcc.record_stream(mfcc_stream)
+                    a.record_stream(cur)
+                else:
+                    a = self.audio_encoder(in_mfcc)
             p = self.aff_encoder(pre_seq[..., :-1])
-            a = self.audio_encoder(in_mfcc) if self.input_context in ('both', 'audio') else None
+            if a is not None and mfcc_stream is not None and in_mfcc.is_cuda:
+                cur.wait_event(done)
         return p, a
 
     def encode_text(self, in_text):

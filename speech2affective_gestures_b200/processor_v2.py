@@ -203,18 +203,27 @@ class Processor(object):
         pre_seq = self.make_pre_seq(target_poses)
         if train:
             ops.advance_seed_nonce(self.device)
+        use_side = self.device.type == "cuda" and self.use_side_stream
+        ev_start = None
+        if use_side:
+            # fork point of the side streams: the inputs are ready and the dropout nonce is advanced; nothing the
+            # main stream launches from here on (the shared encoders first) holds the side streams back
+            ev_start = torch.cuda.Event(); ev_start.record(torch.cuda.current_stream())
+            if self._side_stream_c is None and os.environ.get("S2AG_CONV_WGRAD_STREAM", "1") != "0":
+                self._side_stream_c = torch.cuda.Stream(priority=_prio("side"))
         use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
         # AffEncoder(pre_seq) and MFCCEncoder(in_mfcc) have no dropout and G's weights do not change between the
         # generator passes of one iteration (:798, :823, :909): evaluate them once for all passes.
         n_passes = (1 if gan_on else 0) + 1 + (1 if use_div else 0)
         with torch.set_grad_enabled(train):
-            shared = G.encode_shared(pre_seq, in_mfcc, repeats=n_passes if G.training else 1)
+            shared = G.encode_shared(pre_seq, in_mfcc, repeats=n_passes if G.training else 1,
+                                     mfcc_stream=self._side_stream_c if (use_side and os.environ.get(
+                                         "S2AG_MFCC_STREAM", "1") != "0") else None)
         shared_ng = tuple(None if t is None else t.detach() for t in shared)
         # Input-only encoders (the generator's TextEncoderTCN for each of its passes, the frozen baseline's WavEncoder
         # and TextEncoderTCN) run on a side stream: they overlap the latency-bound recurrent kernels of the main
         # stream, which occupy only about half of the SMs.  Events order each consumer after its producer; autograd
         # runs the backward of the side-stream ops on the side stream and synchronises by itself.
-        use_side = self.device.type == "cuda" and self.use_side_stream
         main_s = torch.cuda.current_stream() if use_side else None
         txt1 = txt2 = txt3 = tri_pre = None
         eps2 = eps3 = early3 = early2 = run_tri_late = out_tri = None
@@ -232,7 +241,10 @@ class Processor(object):
             # (the TCN blocks' weight gradients go to the second side stream: it is idle once the generator's BPTT is done)
             ops.set_side_stream(side, self._side_stream_c,
                                 self._side_stream_b if os.environ.get("S2AG_TCN_WGRAD_STREAM", "b") == "b" else None)
-            side.wait_stream(main_s)
+            if os.environ.get("S2AG_EARLY_FORK", "1") != "0":
+                side.wait_event(ev_start)
+            else:
+                side.wait_stream(main_s)
             if self._side_stream_c is not None:
                 self._side_stream_c.wait_stream(main_s)
             with torch.cuda.stream(side):
