@@ -48,6 +48,18 @@ def _prio(role):
     return table[role]
 
 
+_STREAMS = {}
+
+
+def _stream_for(device, role):
+    """The step's streams are a per-device resource shared by every Processor of the process (each owns a 192 MB
+    packed-operand scratch registered with the library, ops._handle): created once per (device, role)."""
+    key = (torch.device(device).index, role)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(device=device, priority=_prio(role if role in ("main", "side", "sideb") else "side"))
+    return _STREAMS[key]
+
+
 def get_epoch_and_loss(path_to_model_files, epoch='best'):
     """Checkpoint discovery by filename, same scheme as processor_v2.py:53-83:
     epoch_{:06d}_loss_{:.4f}_model.pth.tar; 'best' = lowest loss."""
@@ -210,7 +222,7 @@ class Processor(object):
             # main stream launches from here on (the shared encoders first) holds the side streams back
             ev_start = torch.cuda.Event(); ev_start.record(torch.cuda.current_stream())
             if self._side_stream_c is None and os.environ.get("S2AG_CONV_WGRAD_STREAM", "1") != "0":
-                self._side_stream_c = torch.cuda.Stream(priority=_prio("side"))
+                self._side_stream_c = _stream_for(self.device, "sidec")
         use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
         # AffEncoder(pre_seq) and MFCCEncoder(in_mfcc) have no dropout and G's weights do not change between the
         # generator passes of one iteration (:798, :823, :909): evaluate them once for all passes.
@@ -230,14 +242,14 @@ class Processor(object):
         ev = {}
         if use_side:
             if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(priority=_prio("side"))
+                self._side_stream = _stream_for(self.device, "side")
             side = self._side_stream
             if self._side_stream_c is None and os.environ.get("S2AG_CONV_WGRAD_STREAM", "1") != "0":
-                self._side_stream_c = torch.cuda.Stream(priority=_prio("side"))
+                self._side_stream_c = _stream_for(self.device, "sidec")
             # GRU weight-gradient GEMMs run on `side`, beside the next layer's BPTT kernel; the convolutions' weight
             # gradients on a stream of their own (they would otherwise queue behind the text encoder's backward)
             if self._side_stream_b is None:
-                self._side_stream_b = torch.cuda.Stream(priority=_prio("sideb"))
+                self._side_stream_b = _stream_for(self.device, "sideb")
             # (the TCN blocks' weight gradients go to the second side stream: it is idle once the generator's BPTT is done)
             ops.set_side_stream(side, self._side_stream_c,
                                 self._side_stream_b if os.environ.get("S2AG_TCN_WGRAD_STREAM", "b") == "b" else None)
@@ -281,7 +293,7 @@ class Processor(object):
                 # for it before generator pass #2, so two generator-sized persistent kernels (76 + 76 > 148 SMs) can
                 # never be in flight together.
                 if self._side_stream_b is None:
-                    self._side_stream_b = torch.cuda.Stream(priority=_prio("sideb"))
+                    self._side_stream_b = _stream_for(self.device, "sideb")
                 sb = self._side_stream_b
                 ev_p1 = torch.cuda.Event(); ev_p1.record(main_s)
                 sb.wait_event(ev_p1)
@@ -505,7 +517,7 @@ class Processor(object):
         # the packed-operand contractions is registered for it before the capture starts (ops._handle never allocates
         # during a capture; a stream first seen while capturing would fall back to the unpacked contraction).
         if getattr(self, "_capture_stream", None) is None:
-            self._capture_stream = torch.cuda.Stream(priority=_prio("main"))
+            self._capture_stream = _stream_for(self.device, "main")
         cs = self._capture_stream
         snap = self._snapshot_state() if train else None   # warm-up iterations must not train the live model
         cs.wait_stream(torch.cuda.current_stream())
