@@ -170,8 +170,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   if (blockIdx.y == 0 && ty == 0 && grp == 0) {   // parameter gradients: sum over the groups, one writer
     double sd = 0.0, sx = 0.0;
     for (int q = 0; q < (int)gridDim.z; ++q) { sd += ws[(long)q * 2 * C + c]; sx += ws[(long)q * 2 * C + C + c]; }
-    if (dgamma) dgamma[pi] += (float)sx;
-    if (dbeta) dbeta[pi] += (float)sd;
+    // atomics: two backward chains of the same module may run on different streams (D(real) / D(fake))
+    if (dgamma) atomicAdd(dgamma + pi, (float)sx);
+    if (dbeta) atomicAdd(dbeta + pi, (float)sd);
   }
   dy += grp * M * lddy; x += grp * M * ldx; save_mean += grp * C; save_invstd += grp * C; ws += grp * 2 * C;
   if (y) y += grp * M * ldy;
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(
       const int pi = pmap ? pmap[c] : c;
       double sd = 0.0, sx = 0.0;
       for (int q = 0; q < (int)gridDim.z; ++q) { sd += ws[(long)q * 2 * C + c]; sx += ws[(long)q * 2 * C + C + c]; }
-      if (dgamma) dgamma[pi] += (float)sx;
-      if (dbeta) dbeta[pi] += (float)sd;
+      if (dgamma) atomicAdd(dgamma + pi, (float)sx);
+      if (dbeta) atomicAdd(dbeta + pi, (float)sd);
     }
   }
   if (!dx) return;

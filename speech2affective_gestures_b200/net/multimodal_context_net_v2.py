@@ -510,14 +510,20 @@ class AffDiscriminator(FlatParamNet):
         g = ops.bigru(feat, _gru_param_list(self.gru), 4, self.hidden_size, self.gru.dropout, self.training)
         return ops.dhead(g, self.out.weight, self.out.bias, self.out2.weight, self.out2.bias)
 
-    def forward_pair(self, poses_a, poses_b):
+    def forward_pair(self, poses_a, poses_b, feat_a=None):
         """D(poses_a), D(poses_b) as the reference computes them back to back with the same weights
         (processor_v2.py:808-809).  Nothing but BatchNorm couples the samples of a batch, so both batches go through
         every kernel together: the AffEncoder with per-call BatchNorm statistics (two statistics groups, running
         statistics updated in call order) and ONE latency-bound recurrent launch per GRU layer."""
-        # one pass over both stacked batches; BatchNorm keeps the two calls' statistics apart (ops.bn_groups)
-        with ops.bn_groups(2):
-            feat = self.aff_encoder(torch.cat([poses_a, poses_b], dim=0))
+        if feat_a is not None:
+            # `feat_a` = self.aff_encoder(poses_a) evaluated EARLIER by the caller (D(target) depends on nothing the
+            # generator produces; the caller orders it before this call, so BatchNorm's running statistics still
+            # advance in call order): only the second batch goes through the encoder here
+            feat = torch.cat([feat_a, self.aff_encoder(poses_b)], dim=0)
+        else:
+            # one pass over both stacked batches; BatchNorm keeps the two calls' statistics apart (ops.bn_groups)
+            with ops.bn_groups(2):
+                feat = self.aff_encoder(torch.cat([poses_a, poses_b], dim=0))
         g = ops.bigru(feat, _gru_param_list(self.gru), 4, self.hidden_size, self.gru.dropout, self.training)
         o = ops.dhead(g, self.out.weight, self.out.bias, self.out2.weight, self.out2.bias)
         n = poses_a.shape[0]

@@ -431,7 +431,9 @@ class ConvBnActFn(torch.autograd.Function):
             side = _side_stream_conv[0]
             cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
             wst = st
-            if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:
+            if side is not None and cur is not None and cur != side:
+                # (also when no data gradient follows: every accumulation into a convolution's parameter gradients is
+                # serialised on this one stream, whichever stream the backward chain of the module instance runs on)
                 # the weight gradient is a leaf of the backward graph: it runs on the side stream beside the
                 # data-gradient chain (the caller joins the side stream before it consumes parameter gradients)
                 ev = torch.cuda.Event()
@@ -565,7 +567,7 @@ class GcnFn(torch.autograd.Function):
             side = _side_stream_conv[0]
             cur = torch.cuda.current_stream(dy.device) if dy.is_cuda else None
             wst = st
-            if side is not None and cur is not None and cur != side and ctx.needs_input_grad[0]:
+            if side is not None and cur is not None and cur != side:
                 ev = torch.cuda.Event()   # weight gradient beside the data-gradient chain (see ConvBnActFn.backward)
                 ev.record(cur)
                 side.wait_event(ev)

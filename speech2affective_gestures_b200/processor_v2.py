@@ -168,6 +168,7 @@ class Processor(object):
         self._graph = None
         self._side_stream = None
         self._side_stream_c = None
+        self._side_stream_d = None
         self._side_stream_b = None
         self._copy_stream = None
         self.use_side_stream = True
@@ -223,6 +224,21 @@ class Processor(object):
             ev_start = torch.cuda.Event(); ev_start.record(torch.cuda.current_stream())
             if self._side_stream_c is None and os.environ.get("S2AG_CONV_WGRAD_STREAM", "1") != "0":
                 self._side_stream_c = _stream_for(self.device, "sidec")
+        feat_real = ev_real = None
+        if use_side and gan_on and train and os.environ.get("S2AG_D_REAL_EARLY", "0") == "1":
+            # (opt-in, measured SLOWER: 12.38 vs 11.92 ms/step -- two 256-clip encoder chains cost more than one 512-clip
+            # chain on SMs shared with the persistent kernels.)
+            # D(target)'s AffEncoder (:808) depends on nothing the generator produces: it runs on a stream of its own
+            # from the step's start, beside generator pass #1; autograd runs its backward there too, beside the backward
+            # of D(fake)'s encoder (parameter-gradient accumulations are serialised on the conv weight-gradient stream
+            # or atomic, see ops.ConvBnActFn / csrc/bn.cu)
+            sd_ = self._side_stream_d = _stream_for(self.device, "sided")
+            sd_.wait_event(ev_start)
+            with torch.cuda.stream(sd_):
+                feat_real = D.aff_encoder(target_poses)
+            ev_real = torch.cuda.Event(); ev_real.record(sd_)
+            target_poses.record_stream(sd_)
+            feat_real.record_stream(torch.cuda.current_stream())
         use_div = cfg.z_type in ('speaker', 'random') and cfg.loss_reg_weight > 0.0
         # AffEncoder(pre_seq) and MFCCEncoder(in_mfcc) have no dropout and G's weights do not change between the
         # generator passes of one iteration (:798, :823, :909): evaluate them once for all passes.
@@ -379,13 +395,18 @@ class Processor(object):
                     out_tri = run_tri()
                 elif tri_late:
                     run_tri_late = run_tri
+            if ev_real is not None:
+                main_s.wait_event(ev_real)
             with torch.set_grad_enabled(train):
-                dis_real, dis_fake = D.forward_pair(target_poses, out_for_d)  # == D(target), D(out.detach()) (:808-809)
+                # == D(target), D(out.detach()) (:808-809)
+                dis_real, dis_fake = D.forward_pair(target_poses, out_for_d, feat_a=feat_real)
             g_real, g_fake = ops.dis_loss(dis_real, dis_fake, m[M_DIS:M_DIS + 1], want_grads=train)
             if train:
                 torch.autograd.backward([dis_real, dis_fake], [g_real, g_fake])
                 if use_side:
                     main_s.wait_stream(self._side_stream)  # weight-gradient GEMMs issued on the side streams
+                    if ev_real is not None:
+                        main_s.wait_stream(self._side_stream_d)   # backward of D(target)'s encoder
                     if self._side_stream_c is not None:
                         main_s.wait_stream(self._side_stream_c)
                 self._allreduce_grads(D)
@@ -474,6 +495,8 @@ class Processor(object):
             out_tri = run_tri_late()
         if use_side:
             main_s.wait_stream(self._side_stream)  # join (also required before a graph capture ends)
+            if ev_real is not None:
+                main_s.wait_stream(self._side_stream_d)
             if self._side_stream_c is not None:
                 main_s.wait_stream(self._side_stream_c)
             if self._side_stream_b is not None:
@@ -528,7 +551,7 @@ class Processor(object):
         torch.cuda.synchronize()
         if snap is not None:
             self._restore_state(snap)
-        for st in (cs, self._side_stream, self._side_stream_b, self._side_stream_c):
+        for st in (cs, self._side_stream, self._side_stream_b, self._side_stream_c, getattr(self, "_side_stream_d", None)):
             if st is not None:
                 ops._handle(st, dev)   # registers the packed-operand scratch of a stream the warm-up did not launch on
             assert st is None or ops.has_scratch(st, dev), "a stream of the captured step has no registered scratch"
