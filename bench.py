@@ -148,7 +148,7 @@ def run_reference_arm(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same shapes (profiles/,
 # 256 clips); None where no capture of that kernel is committed
-NCU_TRAFFIC = {"gru_recurrence_fwd": 66.0e6 + 55.6e6,   # profiles/r01_ncu_gru_persist.txt
+NCU_TRAFFIC = {"gru_recurrence_fwd": 65.92e6 + 53.71e6,   # profiles/r02_final_ncu_gru_persist_fwd.txt
                "gemm_gru_projection": 38848512,         # profiles/r01_ncu_gemm_umma_pk.txt
                # profiles/r02_ncu_wavencoder.txt: sum over the four launches (ncu flushes L2 between kernels, so the
                # raw conv2/conv3 intermediates -- L2-resident in a real step -- are counted as DRAM reads here)
