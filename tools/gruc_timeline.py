@@ -56,3 +56,6 @@ print("  step period                avg %8.0f cycles" % (sum(per) / len(per)))
 print("step 10: slice i observed ready (cycles after the worker's start of step 9's copy issue [mark 8 of step 9]):")
 print("  ", [buf[40 * 16 + i] - tl[9][8] for i in range(8)])
 print("   next step start at", tl[10][0] - tl[9][8])
+print("per-step period (cycles), all steps:", [tl[s + 1][0] - tl[s][0] for s in range(T - 1)])
+print("worker marks of step 0 relative to its start:", [tl[0][i] - tl[0][0] for i in range(1, 10)])
+print("worker marks of the last step:", [tl[T - 1][i] - tl[T - 1][0] for i in range(1, 10)])
