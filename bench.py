@@ -150,6 +150,9 @@ def run_reference_arm(args):
 # 256 clips); None where no capture of that kernel is committed
 NCU_TRAFFIC = {"gru_recurrence_fwd": 65.92e6 + 53.71e6,   # profiles/r02_final_ncu_gru_persist_fwd.txt
                "gemm_gru_projection": 38848512,         # profiles/r01_ncu_gemm_umma_pk.txt
+               # profiles/r02_final_ncu_tcn_fused.txt: reads only (x + the weight image); the 10.4 MB output is still
+               # L2-resident when the kernel ends, so DRAM writes are ~0 in the capture
+               "tcn_residual_block_fused_fwd": 11.98e6,
                # profiles/r02_ncu_wavencoder.txt: sum over the four launches (ncu flushes L2 between kernels, so the
                # raw conv2/conv3 intermediates -- L2-resident in a real step -- are counted as DRAM reads here)
                "wavencoder_fwd": 37.45e6 + (37.22e6 + 2.99e6) + (43.21e6 + 0.42e6) + 14.39e6}
