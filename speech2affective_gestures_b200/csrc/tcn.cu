@@ -109,17 +109,35 @@ __global__ void embedding_fwd_kernel(const int64_t* __restrict__ idx, const floa
     out[i * ldo + d] = __ldg(table + r * (long)D + d) * s2ag_dropout_scale(seed, (unsigned long long)e, p);
   }
 }
-__global__ void embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dout, long ldo,
-                                     float* __restrict__ dtable, long n, int D, long V, float p, unsigned long long seed,
-                                     const unsigned long long* __restrict__ seed_dev) {
+// dtable[idx[i]] += dout[i] * dropout mask.  Most positions of a clip hold the SAME token (24 of the 34 frames are the
+// padding id: extend_word_seq leaves zeros between the ~10 words), so per-element atomics serialise thousands of adds on
+// the 300 addresses of one table row (72 us at 256 clips).  A block owns a chunk of consecutive rows and a thread one
+// feature column: it walks the chunk keeping a running sum while the index repeats... and, because the repeats are
+// interleaved with the words, also a second running sum for the chunk's HOT index (taken from the chunk's first rows):
+// rows of the hot index never touch memory until the chunk is done.  Any index may be hot; only the speed depends on it.
+constexpr int kEmbRows = 64;
+__global__ void __launch_bounds__(128) embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dout,
+                                                            long ldo, float* __restrict__ dtable, long n, int D, long V,
+                                                            float p, unsigned long long seed,
+                                                            const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev) seed += seed_dev[0];
-  const long total = n * D;
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const long i = e / D; const int d = (int)(e % D);
-    const float gsc = s2ag_dropout_scale(seed, (unsigned long long)e, p);
-    const long r = idx[i];
-    if (r < 0 || r >= V) S2AG_DEVICE_TRAP();
-    if (gsc != 0.f) atomicAdd(dtable + r * (long)D + d, dout[i * ldo + d] * gsc);
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;   // no barriers in this kernel
+  for (long i0 = (long)blockIdx.x * kEmbRows; i0 < n; i0 += (long)gridDim.x * kEmbRows) {
+    const long i1 = i0 + kEmbRows < n ? i0 + kEmbRows : n;
+    long hot = idx[i0];   // the more frequent of the chunk's first rows
+    if (i0 + 2 < i1 && idx[i0 + 1] == idx[i0 + 2]) hot = idx[i0 + 1];
+    float hot_sum = 0.f;
+    for (long i = i0; i < i1; ++i) {
+      const long r = idx[i];
+      if (r < 0 || r >= V) S2AG_DEVICE_TRAP();
+      const float gsc = s2ag_dropout_scale(seed, (unsigned long long)(i * D + d), p);
+      if (gsc == 0.f) continue;
+      const float v = dout[i * ldo + d] * gsc;
+      if (r == hot) hot_sum += v;
+      else atomicAdd(dtable + r * (long)D + d, v);
+    }
+    if (hot_sum != 0.f) atomicAdd(dtable + hot * (long)D + d, hot_sum);
   }
 }
 
@@ -245,10 +263,10 @@ extern "C" int s2ag_embedding_bwd(const int64_t* idx, const float* dout, long ld
   S2AG_CHECK_ARG(idx && dout && dtable && n >= 0 && D > 0 && V > 0 && ldo >= D && p_drop >= 0.f && p_drop < 1.f);
   long total = n * D;
   if (total == 0) return S2AG_OK;
-  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  long chunks = (n + kEmbRows - 1) / kEmbRows; if (chunks > 148 * 16) chunks = 148 * 16;
   auto kfn = &embedding_bwd_kernel;
-  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, idx, dout, ldo, dtable, n, D, V, p_drop, (unsigned long long)seed,
-              (const unsigned long long*)seed_dev);
+  S2AG_LAUNCH(kfn, dim3((unsigned)chunks, (unsigned)((D + 127) / 128)), 128, 0, stream, idx, dout, ldo, dtable, n, D, V, p_drop,
+              (unsigned long long)seed, (const unsigned long long*)seed_dev);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }

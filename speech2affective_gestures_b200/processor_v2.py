@@ -315,10 +315,15 @@ class Processor(object):
                 sb.wait_event(ev_p1)
                 sb.wait_event(ev['t'])
                 # (the baseline's re-parametrisation noise is drawn here, at its place in the reference's order)
+                # In training every consumer of these draws lives on the second side stream, so the draws (and the sort
+                # behind the speaker permutation, ~45 us of small kernels) are enqueued there and leave the main
+                # stream's serial chain; the generator state advances in program order either way.
+                draw_s = sb if train else main_s
                 eps_t = None
                 if getattr(Tri, 'speaker_embedding', None) is not None:
-                    eps_t = en.draw_eps(torch.empty(vid_indices.shape[0], Tri.z_size, device=self.device))
-                    ev_e = torch.cuda.Event(); ev_e.record(main_s)   # the draw runs on the main stream
+                    with torch.cuda.stream(draw_s):
+                        eps_t = en.draw_eps(torch.empty(vid_indices.shape[0], Tri.z_size, device=self.device))
+                    ev_e = torch.cuda.Event(); ev_e.record(draw_s)
                     sb.wait_event(ev_e)
 
                 def run_tri():
@@ -331,8 +336,8 @@ class Processor(object):
                             t_.record_stream(sb)
                     return o
 
-                # training: generator pass #2, then #3 on this stream beside the D step; the frozen baseline is queued
-                # behind the generator's BPTT (after autograd.backward below), beside the encoders' backward
+                # training (measured order, tools/ab_schedule.sh): generator pass #3, pass #2, then the frozen baseline
+                # ("mid") on this stream beside the D step; "1" queues the baseline behind the generator's BPTT instead
                 tri_mode = os.environ.get("S2AG_TRI_LATE", "mid") if train else "0"   # A/B: "0" first, "1" after the BPTT
                 tri_late = tri_mode != "0"
                 if not tri_late:
@@ -342,11 +347,13 @@ class Processor(object):
                 if use_div and train and cfg.z_type == 'speaker':
                     # the re-parametrisation noise of passes #2 and #3 and the speaker permutation are drawn here, in
                     # the reference's order (:823, :903-909), whatever order the passes are launched in
-                    like = torch.empty(vid_indices.shape[0], G.z_size, device=self.device)
-                    eps2, eps3 = en.draw_eps(like), en.draw_eps(like)
-                    rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
-                        torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
-                    rand_vids = vid_indices[rand_idx]
+                    with torch.cuda.stream(draw_s):
+                        like = torch.empty(vid_indices.shape[0], G.z_size, device=self.device)
+                        eps2, eps3 = en.draw_eps(like), en.draw_eps(like)
+                        rand_idx = self.injected_rand_idx if self.injected_rand_idx is not None else \
+                            torch.rand(vid_indices.shape[0], device=vid_indices.device).argsort()
+                        rand_vids = vid_indices[rand_idx]
+                    vid_indices.record_stream(draw_s)
                 else:
                     rand_vids = None
                 def launch_pass2():

@@ -364,6 +364,27 @@ def test_embedding(dev):
     close(y2[m], (ref.to(dev) / 0.9)[m].detach())
 
 
+@pytest.mark.parametrize("B,p", [(7, 0.0), (5, 0.1), (40, 0.0)])
+def test_embedding_backward_padded_text(dev, B, p):
+    """TED-shaped token grids (24 of 34 positions hold the padding id 0, extend_word_seq): the backward pre-aggregates the
+    chunk's most frequent index before its atomics; row counts that are not a multiple of the 64-row chunk; with dropout the
+    table gradient is the scatter of the upstream gradient through the SAME mask the forward drew"""
+    torch.manual_seed(90 + B)
+    V, D = 80, 300
+    table = torch.randn(V, D)
+    idx = torch.zeros(B, 34, dtype=torch.int64)
+    pos = torch.rand(B, 34).argsort(dim=1)[:, :10]
+    idx.scatter_(1, pos, torch.randint(4, V, (B, 10)))
+    td = P(table, dev)
+    y = ops.embedding(idx.to(dev), td, p)
+    g = torch.randn(B, 34, D)
+    y.backward(g.to(dev))
+    mask = (y.detach().cpu() != 0).float() / (1.0 - p) if p > 0 else torch.ones(B, 34, D)
+    want = torch.zeros(V, D, dtype=torch.float64)
+    want.index_add_(0, idx.reshape(-1), (g * mask).reshape(-1, D).double())
+    close(td.grad, want, tol=1e-5, what="dtable")
+
+
 @pytest.mark.parametrize("In,H,sum_halves", [(24, 40, True), (8, 64, False)])
 def test_bigru(dev, In, H, sum_halves):
     torch.manual_seed(10)
