@@ -336,7 +336,7 @@ class Processor(object):
                             t_.record_stream(sb)
                     return o
 
-                # training (measured order, tools/ab_schedule.sh): generator pass #3, pass #2, then the frozen baseline
+                # training (measured order, tools/ab_schedule.sh / ab_final.sh): generator pass #2, pass #3, then the frozen baseline
                 # ("mid") on this stream beside the D step; "1" queues the baseline behind the generator's BPTT instead
                 tri_mode = os.environ.get("S2AG_TRI_LATE", "mid") if train else "0"   # A/B: "0" first, "1" after the BPTT
                 tri_late = tri_mode != "0"
@@ -391,8 +391,9 @@ class Processor(object):
                         if t_ is not None:
                             t_.record_stream(main_s)
 
-                # order on the side stream (measured, tools/step_timeline.py): pass #3, pass #2, then the baseline
-                order = os.environ.get("S2AG_PASS_ORDER", "32")
+                # order on the side stream (measured, tools/ab_final.sh: 11.76 vs 11.87 ms/step): pass #2, pass #3, then the
+                # baseline -- D(out) on the main stream can start as soon as the D step is done
+                order = os.environ.get("S2AG_PASS_ORDER", "23")
                 for which in order:
                     if which == "2" and train:
                         launch_pass2()
