@@ -190,7 +190,18 @@ int s2ag_graph_bwd(const float* dy, const float* A, float* dx, int M, int V, int
 int s2ag_gcn_compose_fwd(const float* W, const float* b, const float* A, float* Weff, float* beff, int V, int K,
                          int C, int Cin, int Kt, void* stream);
 int s2ag_gcn_compose_bwd(const float* dWeff, const float* dbeff, const float* A, float* dW, float* db, int V,
-                         int K, int C, int Cin, int Kt, void* stream);
+                         int K, int C, int Cin, int Kt, int layout, void* stream);
+/* layout 0: dWeff in the convolution's weight layout [V*C][V*Cin][Kt]; layout 1: dWeffT[Kt*V*Cin][V*C] as written by
+ * s2ag_window_wgrad.
+ * Temporal-convolution weight gradient as a plain contraction over a sliding-window view: x_pad [N, Tp = T + 2p, C] (+ Kt - 1
+ * zero rows; s2ag_pad_time with off = p, tail_rows = Kt - 1), dy_pad [N, Tp, Cout] (off = 0: rows t >= T zero), R = N * Tp:
+ *   dwT[dt*C + c][co] += sum_r x_pad[(r + dt)*C + c] * dy_pad[r*Cout + co]      (Kwin = Kt*C, ldx = C, lddy = Cout) */
+int s2ag_pad_time(const float* src, long ld_src, float* dst, int N, int T, int C, int Tp, int off, int tail_rows,
+                  void* stream);
+int s2ag_window_wgrad(const float* dy_pad, long lddy, const float* x_pad, long ldx, float* dwT, long R, int Cout,
+                      int Kwin, void* stream);
+/* db[N] += column sums of dy[M, N] */
+int s2ag_colsum(const float* dy, long lddy, float* db, int M, int N, void* stream);
 
 /* ---- weight_norm + causal dilated TemporalBlock (net/tcn.py:16-46) ---------------------------
  * weight_norm (old style, dim=0): w[co] = g[co] * v[co] / ||v[co]||.  v is [Co,Ci,k] (reference

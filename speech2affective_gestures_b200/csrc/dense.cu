@@ -234,6 +234,58 @@ __global__ void __launch_bounds__(256) conv1d_direct_kernel(const float* __restr
 // ------------------------------------------------------------------ Conv (channels-last implicit GEMM)
 static inline int conv_out(int L, int k, int s, int p, int d) { return (L + 2 * p - d * (k - 1) - 1) / s + 1; }
 
+// ---- temporal-convolution weight gradient as a PLAIN contraction over a sliding-window view --------------------------
+// For a stride-1 Conv1d over channels-last rows the im2col row of output (n, t) is the contiguous run
+// x_pad[n, t .. t + Kt - 1, :] of the zero-padded input: with x_pad laid out [N, T + 2p, C] (+ Kt - 1 zero rows at the
+// end) and dy_pad [N, T + 2p, Cout] (rows t >= T zero), the gradient is dwT[dt*C + c][co] = sum_r x_pad[(r + dt)*C + c] *
+// dy_pad[r*Cout + co] over ALL R = N (T + 2p) rows: two row-major operands with pitches C and Cout, no gather, no clip
+// boundaries (the windows of the dummy rows t >= T reach into the next clip and are multiplied by zero).  The composed
+// ST-GCN convolution (stgcn.cu) is the user: 48 x 1296 x 17 408 through the transposed-im2col loader cost 140-370 us.
+namespace {
+__global__ void __launch_bounds__(256) pad_time_kernel(const float* __restrict__ src, long ld_src, float* __restrict__ dst,
+                                                       int N, int T, int C, int Tp, int off, long total_rows) {
+  const long total = total_rows * C;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long row = e / C; const int c = (int)(e - row * C);
+    const long n = row / Tp; const int t = (int)(row - n * Tp) - off;
+    dst[e] = (n < N && t >= 0 && t < T) ? __ldg(src + (n * T + t) * ld_src + c) : 0.f;
+  }
+}
+}  // namespace
+
+extern "C" int s2ag_pad_time(const float* src, long ld_src, float* dst, int N, int T, int C, int Tp, int off,
+                             int tail_rows, void* stream) {
+  S2AG_CHECK_ARG(src && dst && N >= 0 && T > 0 && C > 0 && Tp >= T + off && off >= 0 && tail_rows >= 0 && ld_src >= C);
+  const long rows = (long)N * Tp + tail_rows;
+  if (rows == 0) return S2AG_OK;
+  long blocks = (rows * C + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  auto kfn = &pad_time_kernel;
+  S2AG_LAUNCH(kfn, (int)blocks, 256, 0, stream, src, ld_src, dst, N, T, C, Tp, off, rows);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_window_wgrad(const float* dy_pad, long lddy, const float* x_pad, long ldx, float* dwT, long R,
+                                 int Cout, int Kwin, void* stream) {
+  S2AG_CHECK_ARG(dy_pad && x_pad && dwT && R >= 0 && R < (1L << 31) && Cout > 0 && Kwin > 0 && lddy >= Cout && ldx > 0);
+  if (R == 0) return S2AG_OK;
+  // dwT[kcol, co] += sum_r x_pad[r*ldx + kcol] * dy_pad[r*lddy + co]: rows kcol (overlapping windows: ldx < Kwin), cols co
+  LdPlain<false> a{x_pad, 1, ldx, 0};
+  LdPlain<false> b{dy_pad, 1, lddy, 0};
+  int sk = pick_splitk(Kwin, Cout, (int)R, 1);
+  launch_gemm(a, b, make_epi(dwT, (long)Cout, nullptr, 0, 0.f, sk > 1 ? 2 : 1), Kwin, Cout, (int)R, 1, sk, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
+extern "C" int s2ag_colsum(const float* dy, long lddy, float* db, int M, int N, void* stream) {
+  S2AG_CHECK_ARG(dy && db && M >= 0 && N > 0 && lddy >= N);
+  if (M == 0) return S2AG_OK;
+  launch_colsum(dy, lddy, db, M, N, stream);
+  S2AG_CHECK_LAUNCH();
+  return S2AG_OK;
+}
+
 extern "C" int s2ag_conv_fwd(const float* x, long ldpix_x, int N, int H, int W, int Cin,
                              const float* w, const float* bias, float* y, long ldpix_y, int Cout,
                              int KH, int KW, int sh, int sw, int ph, int pw, int dh, int dw,

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) gcn_compose_fwd_kernel(const float* __res
 // dW[k*C + c][ci][dt] += sum_{v,w} A[k][v][w] * dWeff[w*C + c][v*Cin + ci][dt];  db[k*C + c] += sum_w (sum_v A[k][v][w]) dbeff[w*C + c]
 __global__ void __launch_bounds__(256) gcn_compose_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ dbeff,
                                                               const float* __restrict__ A, float* __restrict__ dW,
-                                                              float* __restrict__ db, int V, int K, int C, int Cin, int Kt) {
+                                                              float* __restrict__ db, int V, int K, int C, int Cin, int Kt,
+                                                              int layout) {
   __shared__ float sA[kMaxA];
   for (int i = threadIdx.x; i < K * V * V; i += blockDim.x) sA[i] = A[i];
   __syncthreads();
@@ -95,7 +96,11 @@ __global__ void __launch_bounds__(256) gcn_compose_bwd_kernel(const float* __res
     float acc = 0.f;
     for (int v = 0; v < V; ++v)
       for (int w = 0; w < V; ++w)
-        acc = fmaf(sA[(k * V + v) * V + w], __ldg(dWeff + ((long)(w * C + c) * VCin + v * Cin + ci) * Kt + dt), acc);
+        // layout 0: dWeff[w*C + c][v*Cin + ci][dt] (the convolution's own weight layout);
+        // layout 1: dWeffT[dt*VCin + v*Cin + ci][w*C + c] (s2ag_window_wgrad: window column major)
+        acc = fmaf(sA[(k * V + v) * V + w],
+                   __ldg(layout == 0 ? dWeff + ((long)(w * C + c) * VCin + v * Cin + ci) * Kt + dt
+                                     : dWeff + ((long)dt * VCin + v * Cin + ci) * (V * C) + (w * C + c)), acc);
     dW[i] += acc;
   }
   if (blockIdx.x == 0 && db != nullptr && dbeff != nullptr)
@@ -123,12 +128,13 @@ extern "C" int s2ag_gcn_compose_fwd(const float* W, const float* b, const float*
   return S2AG_OK;
 }
 extern "C" int s2ag_gcn_compose_bwd(const float* dWeff, const float* dbeff, const float* A, float* dW, float* db, int V,
-                                    int K, int C, int Cin, int Kt, void* stream) {
+                                    int K, int C, int Cin, int Kt, int layout, void* stream) {
   S2AG_CHECK_ARG(dWeff && A && dW && V > 0 && K > 0 && C > 0 && Cin > 0 && Kt > 0 && K * V * V <= kMaxA);
   long total = (long)K * C * Cin * Kt;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 4) blocks = 148 * 4;
   auto kfn = &gcn_compose_bwd_kernel;
-  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, dWeff, dbeff, A, dW, db, V, K, C, Cin, Kt);
+  S2AG_CHECK_ARG(layout == 0 || layout == 1);
+  S2AG_LAUNCH(kfn, blocks, 256, 0, stream, dWeff, dbeff, A, dW, db, V, K, C, Cin, Kt, layout);
   S2AG_CHECK_LAUNCH();
   return S2AG_OK;
 }

@@ -530,6 +530,12 @@ def graph_contract(x, A):
     return GraphFn.apply(x, A)
 
 
+# A/B: 1 = weight gradient of the composed convolution as a plain contraction over a sliding-window view of the padded
+# input (s2ag_window_wgrad); parity-tested, measured SLOWER inside the step (11.88 vs 11.72 ms: two padding passes + a
+# 1296-row contraction whose B operand must be packed), so the transposed-im2col route stays the default
+GCN_WGRAD_WINDOW = [os.environ.get("S2AG_GCN_WGRAD_WINDOW", "0") == "1"]
+
+
 class GcnFn(torch.autograd.Function):
     """ConvTemporalGraphical (net/utils/tgcn.py:15-71) as ONE temporal convolution: the (Kt x 1) Conv2d Cin -> K*C and
     einsum('nkctv,kvw->nctw') are composed into a Conv1d over the channels-last rows [N, T, V*Cin] -> [N, T, V*C]
@@ -577,14 +583,31 @@ class GcnFn(torch.autograd.Function):
                 ctxm = torch.cuda.stream(side)
             else:
                 ctxm = contextlib.nullcontext()
-            with ctxm:
-                dweff = torch.zeros_like(weff)
-                dbeff = torch.zeros(V * C, dtype=torch.float32, device=dy.device)
             has_b = b is not None and b.requires_grad
-            _C.call("s2ag_conv_bwd_weight", _p(dy), V * C, _p(x), V * Cin, N, T, 1, V * Cin, _p(dweff), _p(dbeff), V * C,
-                    Kt, 1, 1, 1, pad, 0, 1, 1, wst)
-            _C.call("s2ag_gcn_compose_bwd", _p(dweff), _p(dbeff), _p(A), _p(_grad_of(w)),
-                    _p(_grad_of(b)) if has_b else None, V, K, C, Cin, Kt, wst)
+            if GCN_WGRAD_WINDOW[0] and Kt == 2 * pad + 1:
+                # plain contraction over the sliding-window view of the zero-padded input (s2ag_window_wgrad): no
+                # transposed im2col gather
+                Tp = T + 2 * pad
+                with ctxm:
+                    xp = _empty((N * Tp + Kt - 1, V * Cin), dy)
+                    dyp = _empty((N * Tp, V * C), dy)
+                    dwt = torch.zeros((Kt * V * Cin, V * C), dtype=torch.float32, device=dy.device)
+                    dbeff = torch.zeros(V * C, dtype=torch.float32, device=dy.device)
+                _C.call("s2ag_pad_time", _p(x), V * Cin, _p(xp), N, T, V * Cin, Tp, pad, Kt - 1, wst)
+                _C.call("s2ag_pad_time", _p(dy), V * C, _p(dyp), N, T, V * C, Tp, 0, 0, wst)
+                _C.call("s2ag_window_wgrad", _p(dyp), V * C, _p(xp), V * Cin, _p(dwt), N * Tp, V * C, Kt * V * Cin, wst)
+                if has_b:
+                    _C.call("s2ag_colsum", _p(dy), V * C, _p(dbeff), N * T, V * C, wst)
+                _C.call("s2ag_gcn_compose_bwd", _p(dwt), _p(dbeff), _p(A), _p(_grad_of(w)),
+                        _p(_grad_of(b)) if has_b else None, V, K, C, Cin, Kt, 1, wst)
+            else:
+                with ctxm:
+                    dweff = torch.zeros_like(weff)
+                    dbeff = torch.zeros(V * C, dtype=torch.float32, device=dy.device)
+                _C.call("s2ag_conv_bwd_weight", _p(dy), V * C, _p(x), V * Cin, N, T, 1, V * Cin, _p(dweff), _p(dbeff),
+                        V * C, Kt, 1, 1, 1, pad, 0, 1, 1, wst)
+                _C.call("s2ag_gcn_compose_bwd", _p(dweff), _p(dbeff), _p(A), _p(_grad_of(w)),
+                        _p(_grad_of(b)) if has_b else None, V, K, C, Cin, Kt, 0, wst)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _empty(x.shape, dy)

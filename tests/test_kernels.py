@@ -272,11 +272,13 @@ def test_graph_contract(dev):
     close(y, ref); close(xd.grad, xr.grad, what="dx")
 
 
+@pytest.mark.parametrize("window", [False, True])
 @pytest.mark.parametrize("V,Cin,B", [(9, 3, 2), (3, 48, 2), (9, 3, 33)])
-def test_gcn_composed_conv(dev, V, Cin, B):
+def test_gcn_composed_conv(dev, V, Cin, B, window, monkeypatch):
     """ConvTemporalGraphical as one composed temporal convolution (ops.GcnFn) vs Conv2d((9,1)) + einsum of the reference
     (net/utils/tgcn.py:52-69): output, input gradient, gradients of the ORIGINAL conv parameters (accumulated: a second
     backward doubles them)"""
+    monkeypatch.setitem(ops.GCN_WGRAD_WINDOW, 0, window)   # both weight-gradient routes (ops.GcnFn.backward)
     torch.manual_seed(60 + V)
     T, K, C = 34, 5, 16
     conv = nn.Conv2d(Cin, K * C, (9, 1), padding=(4, 0))
