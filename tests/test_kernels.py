@@ -278,7 +278,7 @@ def test_gcn_composed_conv(dev, V, Cin, B, window, monkeypatch):
     """ConvTemporalGraphical as one composed temporal convolution (ops.GcnFn) vs Conv2d((9,1)) + einsum of the reference
     (net/utils/tgcn.py:52-69): output, input gradient, gradients of the ORIGINAL conv parameters (accumulated: a second
     backward doubles them)"""
-    monkeypatch.setitem(ops.GCN_WGRAD_WINDOW, 0, window)   # both weight-gradient routes (ops.GcnFn.backward)
+    monkeypatch.setattr(ops, "GCN_WGRAD_WINDOW", [window])   # both weight-gradient routes (ops.GcnFn.backward)
     torch.manual_seed(60 + V)
     T, K, C = 34, 5, 16
     conv = nn.Conv2d(Cin, K * C, (9, 1), padding=(4, 0))
