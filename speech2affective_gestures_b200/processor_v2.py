@@ -40,11 +40,13 @@ M_DIS, M_HUBER, M_GEN, M_KLD, M_DIV, M_TOTAL, M_L1, M_L1_TRI = range(8)
 def _prio(role):
     """Stream priorities of the captured step (CUDA: lower number = scheduled first when SMs free up).  The main stream
     carries the serial D step / D(out) / loss chain of short kernels; the side streams carry wide, latency-tolerant
-    work (weight-gradient GEMMs, the other generator passes) that must not starve it.  S2AG_STREAM_PRIO="m,a,b"
-    overrides (A/B measurements)."""
-    env = os.environ.get("S2AG_STREAM_PRIO")
-    table = dict(zip(("main", "side", "sideb"), (int(v) for v in env.split(",")))) if env else \
-        dict(main=-1, side=0, sideb=0)   # measured: 12.94 -> 12.50 ms/step (tools/ab_schedule.sh)
+    work (weight-gradient GEMMs, the other generator passes) that must not starve it.  S2AG_STREAM_PRIO="m,a,b[,c]"
+    overrides (A/B measurements: raising any side stream to the main stream's priority costs 0.05-0.6 ms/step)."""
+    env = os.environ.get("S2AG_STREAM_PRIO")   # "main,side,sideb[,sidec]"
+    table = dict(main=-1, side=0, sideb=0)   # measured: 12.94 -> 12.50 ms/step (tools/ab_schedule.sh)
+    if env:
+        table.update(zip(("main", "side", "sideb", "sidec"), (int(v) for v in env.split(","))))
+    table.setdefault("sidec", table["side"])
     return table[role]
 
 
@@ -56,7 +58,7 @@ def _stream_for(device, role):
     packed-operand scratch registered with the library, ops._handle): created once per (device, role)."""
     key = (torch.device(device).index, role)
     if key not in _STREAMS:
-        _STREAMS[key] = torch.cuda.Stream(device=device, priority=_prio(role if role in ("main", "side", "sideb") else "side"))
+        _STREAMS[key] = torch.cuda.Stream(device=device, priority=_prio(role if role in ("main", "side", "sideb", "sidec") else "side"))
     return _STREAMS[key]
 
 
